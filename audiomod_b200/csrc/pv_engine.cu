@@ -1,0 +1,780 @@
+// Host engine + C ABI (include/pvgpu.h) over the kernels in pv_kernels.cu.
+//
+// The reference processes one stream, slice by slice, on one CPU thread
+// (src/phasevocoder/phasevocoderimpl.cc:340-369 -> phasevocoderprocess.cc:236-376).  Here the
+// data-independent part of that loop (pv_plan.cc) runs once on the host, and the data-dependent part runs as
+// kernels over [rows x frames] tiles; only the phase recursion is serial in time.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pvgpu.h"
+#include "pv_kernels.cuh"
+#include "pv_plan.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace pvgpu {
+
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? PVGPU_ENOMEM : PVGPU_ECUDA, \
+                                           "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// RAII device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+static Config to_config(const pvgpu_config &c) {
+    Config k;
+    k.sample_rate = c.sample_rate; k.channels = c.channels; k.time_ratio = c.time_ratio; k.pitch_semitones = c.pitch_semitones;
+    k.mode = c.mode; k.coremode = c.coremode; k.fftsize = c.fftsize; k.hopsize = c.hopsize;
+    return k;
+}
+
+static int validate(const pvgpu_config *cfg) {
+    if (!cfg) return fail(PVGPU_EINVAL, "null config");
+    if (cfg->channels < 1 || cfg->channels > 16) return fail(PVGPU_EINVAL, "channels must be 1..16");
+    if (cfg->sample_rate < 1000) return fail(PVGPU_EINVAL, "sample_rate too small");
+    if (cfg->fftsize < 16 || cfg->fftsize > 16384) return fail(PVGPU_EINVAL, "fftsize must be 16..16384");
+    return PVGPU_OK;
+}
+
+static void fill_info(const Derived &d, pvgpu_info *info) {
+    info->fftsize = d.N; info->hop = d.hop; info->bins = d.H;
+    info->pitch_scale = d.pitch_scale; info->hs_ratio = d.hs;
+    info->resampler_active = d.rs.active ? 1 : 0;
+    info->resampler_filt_len = (int)d.rs.filt_len;
+    info->resampler_num = d.rs.num; info->resampler_den = d.rs.den;
+    info->outbuf_capacity = d.outbuf_cap;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipeline: device tables + launch sequence for a range of frames
+// ------------------------------------------------------------------------------------------------
+struct Pipeline {
+    Derived d;
+    Tables t;
+    DevPlan p{};
+    int device = 0;
+    DevBuf b_window, b_twf, b_twi, b_stwf, b_stwi, b_perm, b_omega, b_rstab;
+    // schedule on the device
+    DevBuf b_recs, b_norm, b_whisper, b_carmag, b_carph;
+    long recs_base = 0, recs_count = 0;
+    int64_t norm_base = 0;
+    int64_t launches = 0;
+
+    int init(const pvgpu_config &cfg) {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(PVGPU_ECUDA, "no CUDA device: the phase vocoder has no CPU fallback");
+        if (cfg.device < 0 || cfg.device >= ndev) return fail(PVGPU_EINVAL, "device %d out of range (%d devices)", cfg.device, ndev);
+        device = cfg.device;
+        CU(cudaSetDevice(device));
+        d = derive(to_config(cfg));
+        if (d.hop < 1 || d.hop > d.N) return fail(PVGPU_EINVAL, "derived hop %d invalid for fft size %d", d.hop, d.N);
+        t = make_tables(d.N, d.hop);
+        if ((int)t.radix.size() > kMaxStages) return fail(PVGPU_EINVAL, "fft size too large");
+        CU(configure_kernels());
+        p.N = d.N; p.H = d.H; p.half = d.N / 2; p.nc = d.N / 2; p.hop = d.hop;
+        p.Hp = (d.H + 3) & ~3;
+        p.nstages = (int)t.radix.size();
+        for (int i = 0; i < p.nstages; ++i) { p.radix[i] = t.radix[i]; p.span[i] = t.span[i]; }
+        p.inv_n = 1.f / d.N;
+        p.two_pi_hop = 2 * M_PI * (size_t)d.hop;
+        p.freq_comp = d.freq_comp;
+        p.fixed_gain = d.fixed_gain;
+        p.rs_active = (d.rs.active && !d.vocoder) ? 1 : 0;
+        p.rs_direct = d.rs.direct ? 1 : 0;
+        p.rs_num = d.rs.num; p.rs_den = d.rs.den; p.rs_filt_len = d.rs.filt_len; p.rs_oversample = d.rs.oversample;
+        p.rs_int_adv = d.rs.int_adv; p.rs_frac_adv = d.rs.frac_adv;
+        p.rs_table_len = (int)d.rs.table.size();
+        int rc;
+        if ((rc = upload(b_window, t.window.data(), sizeof(float) * t.window.size()))) return rc;
+        if ((rc = upload(b_twf, t.tw_fwd.data(), sizeof(float) * t.tw_fwd.size()))) return rc;
+        if ((rc = upload(b_twi, t.tw_inv.data(), sizeof(float) * t.tw_inv.size()))) return rc;
+        if ((rc = upload(b_stwf, t.stw_fwd.data(), sizeof(float) * t.stw_fwd.size()))) return rc;
+        if ((rc = upload(b_stwi, t.stw_inv.data(), sizeof(float) * t.stw_inv.size()))) return rc;
+        if ((rc = upload(b_perm, t.perm.data(), sizeof(uint16_t) * t.perm.size()))) return rc;
+        if ((rc = upload(b_omega, t.omega.data(), sizeof(float) * t.omega.size()))) return rc;
+        if (p.rs_active && (rc = upload(b_rstab, d.rs.table.data(), sizeof(float) * d.rs.table.size()))) return rc;
+        p.window = b_window.as<float>();
+        p.tw_fwd = b_twf.as<float2>(); p.tw_inv = b_twi.as<float2>();
+        p.stw_fwd = b_stwf.as<float2>(); p.stw_inv = b_stwi.as<float2>();
+        p.perm = b_perm.as<uint16_t>();
+        p.omega = b_omega.as<float>();
+        p.rs_table = b_rstab.as<float>();
+        return PVGPU_OK;
+    }
+
+    static int upload(DevBuf &b, const void *src, size_t bytes) {
+        CU(b.ensure(bytes ? bytes : 4));
+        if (bytes) CU(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
+        return PVGPU_OK;
+    }
+
+    int max_peaks() const { return p.half / 3 + 2; }
+
+    // Upload the slice records [first, first+count) and the normalisers from norm_first on.
+    int upload_schedule(const Scheduler &s, cudaStream_t st) {
+        const auto &recs = s.recs();
+        const auto &norm = s.norm();
+        CU(b_recs.ensure(sizeof(SliceRec) * std::max<size_t>(recs.size(), 1)));
+        CU(b_norm.ensure(sizeof(float) * std::max<size_t>(norm.size(), 1)));
+        if (!recs.empty()) CU(cudaMemcpyAsync(b_recs.p, recs.data(), sizeof(SliceRec) * recs.size(), cudaMemcpyHostToDevice, st));
+        if (!norm.empty()) CU(cudaMemcpyAsync(b_norm.p, norm.data(), sizeof(float) * norm.size(), cudaMemcpyHostToDevice, st));
+        recs_base = s.recs_base();
+        recs_count = (long)recs.size();
+        norm_base = s.norm_base();
+        return PVGPU_OK;
+    }
+
+    // whisper phases for slices [0, n_slices): 2*pi*rand()/RAND_MAX, slice-major, channel, bin (:814-822)
+    int build_whisper(long n_slices) {
+        const size_t n = (size_t)n_slices * d.cfg.channels * d.H;
+        std::vector<int32_t> r(n);
+        glibc_rand_fresh(r.data(), n);
+        std::vector<float> ph(n);
+        const float two_pi = 2 * M_PI;
+        for (size_t i = 0; i < n; ++i) ph[i] = two_pi * (float)r[i] / (float)2147483647;
+        return upload(b_whisper, ph.data(), sizeof(float) * n);
+    }
+
+    // Frames [k0, k0+nf) of the rows in g; the schedule for them must be on the device.
+    void run_frames(const DevRows &g, long k0, int nf, cudaStream_t st) {
+        const SliceRec *recs = b_recs.as<SliceRec>();
+        launch_analyse(p, g, k0, nf, st); ++launches;
+        if (d.robotic) { launch_fixed_phase(p, g, nullptr, k0, nf, st); ++launches; }
+        else if (d.whisper) { launch_fixed_phase(p, g, b_whisper.as<float>(), k0, nf, st); ++launches; }
+        else if (!d.vocoder && !d.constant_mode) { launch_phase_core(p, g, d.cfg.coremode, recs, recs_base, k0, nf, st); ++launches; }
+        launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st); ++launches;
+        launch_overlap_add(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, st); ++launches;
+        if (p.rs_active) { launch_resample(p, g, recs, recs_base, k0, nf, st); ++launches; }
+    }
+};
+
+// Device workspace for a group of rows.
+struct Workspace {
+    DevBuf mag, phase, frames, res, prev_phase, prev_out, peaks, first, n_in, n_out;
+    int rows = 0, F = 0, Fr = 0;
+    int64_t res_stride = 0;
+
+    int ensure(const Pipeline &pl, int rows_, int F_, int halo, int64_t res_len) {
+        const DevPlan &p = pl.p;
+        rows = rows_; F = F_; Fr = F_ + halo;
+        res_stride = (res_len + 3) & ~(int64_t)3;
+        const int streams = rows / pl.d.cfg.channels;
+        CU(mag.ensure(sizeof(float) * (size_t)rows * F * p.Hp));
+        CU(phase.ensure(sizeof(float) * (size_t)rows * F * p.Hp));
+        CU(frames.ensure(sizeof(float) * (size_t)rows * Fr * p.N));
+        if (p.rs_active) CU(res.ensure(sizeof(float) * (size_t)rows * res_stride));
+        CU(prev_phase.ensure(sizeof(float) * (size_t)rows * p.half));
+        CU(prev_out.ensure(sizeof(float) * (size_t)rows * p.half));
+        CU(peaks.ensure(sizeof(int) * (size_t)streams * (1 + pl.max_peaks())));
+        CU(first.ensure(sizeof(int) * (size_t)streams));
+        return PVGPU_OK;
+    }
+
+    int reset_state(const Pipeline &pl, cudaStream_t st) {
+        const DevPlan &p = pl.p;
+        const int streams = rows / pl.d.cfg.channels;
+        CU(cudaMemsetAsync(prev_phase.p, 0, sizeof(float) * (size_t)rows * p.half, st));
+        CU(cudaMemsetAsync(prev_out.p, 0, sizeof(float) * (size_t)rows * p.half, st));
+        CU(cudaMemsetAsync(peaks.p, 0, sizeof(int) * (size_t)streams * (1 + pl.max_peaks()), st));
+        std::vector<int> ones(streams, 1);
+        CU(cudaMemcpyAsync(first.p, ones.data(), sizeof(int) * streams, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // `ones` is a temporary
+        return PVGPU_OK;
+    }
+
+    void bind(const Pipeline &pl, DevRows &g) const {
+        g.mag = mag.as<float>(); g.phase = phase.as<float>(); g.F = F;
+        g.frames = frames.as<float>(); g.Fr = Fr;
+        g.res = res.as<float>(); g.res_stride = res_stride; g.res_base = 0;
+        g.prev_phase = prev_phase.as<float>(); g.prev_out = prev_out.as<float>();
+        g.peaks = peaks.as<int>(); g.maxpk = pl.max_peaks(); g.first_flag = first.as<int>();
+    }
+};
+
+static int halo_of(const std::vector<SliceRec> &recs, long recs_base) {
+    long h = 1;
+    for (size_t i = 0; i < recs.size(); ++i) h = std::max(h, recs_base + (long)i - recs[i].jlo + 1);
+    return (int)h;
+}
+
+}  // namespace pvgpu
+
+using namespace pvgpu;
+
+// ------------------------------------------------------------------------------------------------
+// batch
+// ------------------------------------------------------------------------------------------------
+struct pvgpu_batch {
+    pvgpu_config cfg{};
+    Pipeline pl;
+    int n_streams = 0;
+    int64_t max_in = 0;
+    bool planned = false;
+    std::vector<int64_t> n_in, n_out;
+    long n_slices = 0;
+    int halo = 1;
+    int64_t res_total = 0, out_total = 0;
+    int frames_per_chunk = 64, rows_per_group = 0;
+    Workspace ws;
+    DevBuf d_nin, d_nout, d_stage_in, d_stage_out;
+    cudaStream_t stream = nullptr;
+    int64_t h2d = 0, d2h = 0;
+    ~pvgpu_batch() { if (stream) cudaStreamDestroy(stream); }
+};
+
+extern "C" {
+
+const char *pvgpu_last_error(void) { return g_err.c_str(); }
+int pvgpu_version(void) { return 100; }
+
+int pvgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pvgpu_describe(const pvgpu_config *cfg, pvgpu_info *info) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!info) return fail(PVGPU_EINVAL, "null info");
+    fill_info(derive(to_config(*cfg)), info);
+    return PVGPU_OK;
+}
+
+int pvgpu_plan_counts(const pvgpu_config *cfg, int64_t n_in, int block, int64_t *n_out, int64_t *n_slices, int64_t *n_dropped) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (n_in < 0) return fail(PVGPU_EINVAL, "negative length");
+    Scheduler sc(derive(to_config(*cfg)), false);
+    const StreamPlan sp = plan_stream(sc, (long)n_in, block);
+    if (n_out) *n_out = sp.n_out;
+    if (n_slices) *n_slices = sp.n_slices;
+    if (n_dropped) *n_dropped = sc.dropped();
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_create(const pvgpu_config *cfg, int n_streams, int64_t max_in_samples, pvgpu_batch **out) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!out || n_streams < 1 || max_in_samples < 0) return fail(PVGPU_EINVAL, "bad batch arguments");
+    std::unique_ptr<pvgpu_batch> b(new (std::nothrow) pvgpu_batch);
+    if (!b) return fail(PVGPU_ENOMEM, "out of host memory");
+    b->cfg = *cfg;
+    b->n_streams = n_streams;
+    b->max_in = max_in_samples;
+    if ((rc = b->pl.init(*cfg))) return rc;
+    CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    *out = b.release();
+    return PVGPU_OK;
+}
+
+void pvgpu_batch_destroy(pvgpu_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->pl.device);
+    delete b;
+}
+
+int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info) {
+    if (!b || !info) return fail(PVGPU_EINVAL, "null argument");
+    fill_info(b->pl.d, info);
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group) {
+    if (!b) return fail(PVGPU_EINVAL, "null batch");
+    if (frames_per_chunk > 0) b->frames_per_chunk = frames_per_chunk;
+    if (rows_per_group > 0) b->rows_per_group = rows_per_group;
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_out) {
+    if (!b || !n_in) return fail(PVGPU_EINVAL, "null argument");
+    CU(cudaSetDevice(b->pl.device));
+    Pipeline &pl = b->pl;
+    const int C = b->cfg.channels;
+    int64_t longest = 0;
+    for (int s = 0; s < b->n_streams; ++s) {
+        if (n_in[s] < 0 || n_in[s] > b->max_in) return fail(PVGPU_EINVAL, "stream %d: length %lld outside [0, %lld]", s, (long long)n_in[s], (long long)b->max_in);
+        longest = std::max(longest, n_in[s]);
+    }
+    // one schedule (with normalisers) for the longest stream; every other length only needs its counts
+    Scheduler main_sched(pl.d, true);
+    const StreamPlan mp = plan_stream(main_sched, (long)longest, block);
+    std::map<int64_t, StreamPlan> by_len;
+    by_len[longest] = mp;
+    b->n_in.assign(n_in, n_in + b->n_streams);
+    b->n_out.resize(b->n_streams);
+    for (int s = 0; s < b->n_streams; ++s) {
+        auto it = by_len.find(n_in[s]);
+        if (it == by_len.end()) {
+            Scheduler cnt(pl.d, false);
+            it = by_len.emplace(n_in[s], plan_stream(cnt, (long)n_in[s], block)).first;
+        }
+        b->n_out[s] = it->second.n_out;
+        if (n_out) n_out[s] = it->second.n_out;
+    }
+    if (main_sched.dropped() != 0) return fail(PVGPU_ESTATE, "schedule dropped slices; use a smaller block");
+    b->n_slices = mp.n_slices;
+    b->res_total = main_sched.res_total();
+    b->out_total = main_sched.total_out();
+    b->halo = halo_of(main_sched.recs(), main_sched.recs_base());
+    int rc;
+    if ((rc = pl.upload_schedule(main_sched, nullptr))) return rc;
+    if (pl.d.whisper && (rc = pl.build_whisper(b->n_slices))) return rc;
+    // per-row limits
+    std::vector<int64_t> rin((size_t)b->n_streams * C), rout((size_t)b->n_streams * C);
+    for (int s = 0; s < b->n_streams; ++s)
+        for (int c = 0; c < C; ++c) { rin[(size_t)s * C + c] = b->n_in[s]; rout[(size_t)s * C + c] = b->n_out[s]; }
+    if ((rc = Pipeline::upload(b->d_nin, rin.data(), sizeof(int64_t) * rin.size()))) return rc;
+    if ((rc = Pipeline::upload(b->d_nout, rout.data(), sizeof(int64_t) * rout.size()))) return rc;
+    if (pl.d.vocoder && b->n_slices > 0) {
+        // the carrier pulse train is the same for every stream and channel: analyse it once
+        const long n_car = mp.n_fed;
+        std::vector<float> car((size_t)std::max<long>(n_car, 1));
+        carrier_signal(b->cfg.sample_rate, b->cfg.mode == PVGPU_VOCODER_CHORD, car.data(), (size_t)n_car);
+        DevBuf d_car, d_len;
+        if ((rc = Pipeline::upload(d_car, car.data(), sizeof(float) * car.size()))) return rc;
+        const int64_t len = n_car;
+        if ((rc = Pipeline::upload(d_len, &len, sizeof len))) return rc;
+        CU(pl.b_carmag.ensure(sizeof(float) * (size_t)b->n_slices * pl.p.Hp));
+        CU(pl.b_carph.ensure(sizeof(float) * (size_t)b->n_slices * pl.p.Hp));
+        DevRows g{};
+        g.rows = 1; g.channels = 1;
+        g.in = d_car.as<float>(); g.in_stride = 0; g.in_base = 0; g.n_in = d_len.as<int64_t>();
+        g.mag = pl.b_carmag.as<float>(); g.phase = pl.b_carph.as<float>(); g.F = (int)b->n_slices;
+        launch_analyse(pl.p, g, 0, (int)b->n_slices, nullptr);
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+    }
+    CU(cudaDeviceSynchronize());
+    b->planned = true;
+    return PVGPU_OK;
+}
+
+static int batch_run_group(pvgpu_batch *b, const float *d_in, int64_t in_stride, float *d_out, int64_t out_stride, int row0, int rows,
+                           cudaStream_t st) {
+    Pipeline &pl = b->pl;
+    int rc;
+    if ((rc = b->ws.reset_state(pl, st))) return rc;
+    DevRows g{};
+    g.rows = rows; g.channels = b->cfg.channels;
+    g.in = d_in + (int64_t)row0 * in_stride; g.in_stride = in_stride; g.in_base = 0;
+    g.n_in = b->d_nin.as<int64_t>() + row0;
+    g.n_out = b->d_nout.as<int64_t>() + row0;
+    g.out = d_out + (int64_t)row0 * out_stride; g.out_stride = out_stride; g.out_base = 0;
+    b->ws.bind(pl, g);
+    const int F = b->ws.F;
+    for (long k0 = 0; k0 < b->n_slices; k0 += F) {
+        const int nf = (int)std::min<long>(F, b->n_slices - k0);
+        pl.run_frames(g, k0, nf, st);
+    }
+    CU(cudaGetLastError());
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt, void *cuda_stream) {
+    if (!b || !d_in || !d_out) return fail(PVGPU_EINVAL, "null argument");
+    if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
+    if (fmt != PVGPU_F32) return fail(PVGPU_EINVAL, "device runs take float32 rows");
+    CU(cudaSetDevice(b->pl.device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
+    const int C = b->cfg.channels;
+    const int total_rows = b->n_streams * C;
+    int group = b->rows_per_group > 0 ? b->rows_per_group : total_rows;
+    group = std::max(C, (group / C) * C);
+    group = std::min(group, total_rows);
+    int rc;
+    if ((rc = b->ws.ensure(b->pl, group, b->frames_per_chunk, b->halo, b->res_total))) return rc;
+    b->pl.launches = 0;
+    for (int row0 = 0; row0 < total_rows; row0 += group) {
+        const int rows = std::min(group, total_rows - row0);
+        if ((rc = batch_run_group(b, (const float *)d_in, in_stride, (float *)d_out, out_stride, row0, rows, st))) return rc;
+    }
+    if (!cuda_stream) CU(cudaStreamSynchronize(st));
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt) {
+    if (!b || !in_rows || !out_rows) return fail(PVGPU_EINVAL, "null argument");
+    if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
+    if (fmt != PVGPU_F32) return fail(PVGPU_EINVAL, "only float32 rows are supported");
+    CU(cudaSetDevice(b->pl.device));
+    const int C = b->cfg.channels;
+    const int total_rows = b->n_streams * C;
+    int64_t in_stride = 0, out_stride = 0;
+    for (int s = 0; s < b->n_streams; ++s) { in_stride = std::max(in_stride, b->n_in[s]); out_stride = std::max(out_stride, b->n_out[s]); }
+    in_stride = std::max<int64_t>((in_stride + 3) & ~(int64_t)3, 4);
+    out_stride = std::max<int64_t>((out_stride + 3) & ~(int64_t)3, 4);
+    CU(b->d_stage_in.ensure(sizeof(float) * (size_t)total_rows * in_stride));
+    CU(b->d_stage_out.ensure(sizeof(float) * (size_t)total_rows * out_stride));
+    b->h2d = b->d2h = 0;
+    for (int r = 0; r < total_rows; ++r) {
+        const int64_t n = b->n_in[r / C];
+        if (n) CU(cudaMemcpyAsync(b->d_stage_in.as<float>() + (int64_t)r * in_stride, in_rows[r], sizeof(float) * n, cudaMemcpyHostToDevice, b->stream));
+        b->h2d += sizeof(float) * n;
+    }
+    int rc = pvgpu_batch_run_device(b, b->d_stage_in.p, in_stride, b->d_stage_out.p, out_stride, fmt, b->stream);
+    if (rc) return rc;
+    for (int r = 0; r < total_rows; ++r) {
+        const int64_t n = b->n_out[r / C];
+        if (n) CU(cudaMemcpyAsync(out_rows[r], b->d_stage_out.as<float>() + (int64_t)r * out_stride, sizeof(float) * n, cudaMemcpyDeviceToHost, b->stream));
+        b->d2h += sizeof(float) * n;
+    }
+    CU(cudaStreamSynchronize(b->stream));
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_stats(const pvgpu_batch *b, int64_t *kernel_launches, int64_t *slices, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!b) return fail(PVGPU_EINVAL, "null batch");
+    if (kernel_launches) *kernel_launches = b->pl.launches;
+    if (slices) *slices = b->n_slices;
+    if (h2d_bytes) *h2d_bytes = b->h2d;
+    if (d2h_bytes) *d2h_bytes = b->d2h;
+    return PVGPU_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// stage hooks for the parity tests
+// ------------------------------------------------------------------------------------------------
+static int stage_pipeline(Pipeline &pl, int device, int fftsize) {
+    pvgpu_config cfg{};
+    cfg.sample_rate = 44100; cfg.channels = 1; cfg.time_ratio = 1.f; cfg.pitch_semitones = 0.f;
+    cfg.mode = PVGPU_ROBOTIC; cfg.coremode = 1; cfg.fftsize = fftsize; cfg.hopsize = fftsize; cfg.device = device;
+    int rc = validate(&cfg);
+    if (rc) return rc;
+    if (fftsize & (fftsize - 1)) return fail(PVGPU_EINVAL, "stage hooks need a power-of-two fft size");
+    return pl.init(cfg);
+}
+
+extern "C" {
+
+int pvgpu_test_forward_polar(int device, int fftsize, int n_frames, const float *frames, float *mag, float *phase) {
+    if (!frames || !mag || !phase || n_frames < 1) return fail(PVGPU_EINVAL, "bad argument");
+    Pipeline pl;
+    int rc = stage_pipeline(pl, device, fftsize);
+    if (rc) return rc;
+    const int N = pl.p.N, H = pl.p.H, Hp = pl.p.Hp;
+    DevBuf d_in, d_mag, d_ph, d_len;
+    const int64_t len = (int64_t)n_frames * N;
+    if ((rc = Pipeline::upload(d_in, frames, sizeof(float) * len))) return rc;
+    if ((rc = Pipeline::upload(d_len, &len, sizeof len))) return rc;
+    CU(d_mag.ensure(sizeof(float) * (size_t)n_frames * Hp));
+    CU(d_ph.ensure(sizeof(float) * (size_t)n_frames * Hp));
+    DevRows g{};
+    g.rows = 1; g.channels = 1; g.in = d_in.as<float>(); g.in_stride = len; g.n_in = d_len.as<int64_t>();
+    g.mag = d_mag.as<float>(); g.phase = d_ph.as<float>(); g.F = n_frames;
+    launch_analyse(pl.p, g, 0, n_frames, nullptr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy2D(mag, sizeof(float) * H, d_mag.p, sizeof(float) * Hp, sizeof(float) * H, n_frames, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy2D(phase, sizeof(float) * H, d_ph.p, sizeof(float) * Hp, sizeof(float) * H, n_frames, cudaMemcpyDeviceToHost));
+    return PVGPU_OK;
+}
+
+int pvgpu_test_inverse_polar(int device, int fftsize, int n_frames, const float *mag, const float *phase, float *frames) {
+    if (!frames || !mag || !phase || n_frames < 1) return fail(PVGPU_EINVAL, "bad argument");
+    Pipeline pl;
+    int rc = stage_pipeline(pl, device, fftsize);
+    if (rc) return rc;
+    const int N = pl.p.N, H = pl.p.H, Hp = pl.p.Hp;
+    DevBuf d_mag, d_ph, d_fr;
+    CU(d_mag.ensure(sizeof(float) * (size_t)n_frames * Hp));
+    CU(d_ph.ensure(sizeof(float) * (size_t)n_frames * Hp));
+    CU(d_fr.ensure(sizeof(float) * (size_t)n_frames * N));
+    CU(cudaMemcpy2D(d_mag.p, sizeof(float) * Hp, mag, sizeof(float) * H, sizeof(float) * H, n_frames, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy2D(d_ph.p, sizeof(float) * Hp, phase, sizeof(float) * H, sizeof(float) * H, n_frames, cudaMemcpyHostToDevice));
+    DevRows g{};
+    g.rows = 1; g.channels = 1;
+    g.mag = d_mag.as<float>(); g.phase = d_ph.as<float>(); g.F = n_frames;
+    g.frames = d_fr.as<float>(); g.Fr = n_frames;
+    launch_synthesise(pl.p, g, nullptr, nullptr, 0, n_frames, nullptr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(frames, d_fr.p, sizeof(float) * (size_t)n_frames * N, cudaMemcpyDeviceToHost));
+    return PVGPU_OK;
+}
+
+int pvgpu_test_atan2f(int device, int64_t n, const float *y, const float *x, float *out) {
+    if (!y || !x || !out || n < 1) return fail(PVGPU_EINVAL, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return fail(PVGPU_ECUDA, "no CUDA device");
+    CU(cudaSetDevice(device));
+    DevBuf dy, dx, dout;
+    int rc;
+    if ((rc = Pipeline::upload(dy, y, sizeof(float) * n))) return rc;
+    if ((rc = Pipeline::upload(dx, x, sizeof(float) * n))) return rc;
+    CU(dout.ensure(sizeof(float) * n));
+    launch_test_atan2f(n, dy.as<float>(), dx.as<float>(), dout.as<float>(), nullptr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return PVGPU_OK;
+}
+
+int pvgpu_test_princarg(int device, int64_t n, const double *a, double *out) {
+    if (!a || !out || n < 1) return fail(PVGPU_EINVAL, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device >= ndev) return fail(PVGPU_ECUDA, "no CUDA device");
+    CU(cudaSetDevice(device));
+    DevBuf da, dout;
+    int rc;
+    if ((rc = Pipeline::upload(da, a, sizeof(double) * n))) return rc;
+    CU(dout.ensure(sizeof(double) * n));
+    launch_test_princarg(n, da.as<double>(), dout.as<double>(), nullptr);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, dout.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return PVGPU_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// streaming instance: one audiomod::phasevocoder object.  Each process call appends the new input,
+// lets the scheduler decide which slices that call runs (exactly the reference's block loop), runs
+// those frames on the device and moves the produced samples into a host FIFO.
+// ------------------------------------------------------------------------------------------------
+struct pvgpu_stream {
+    pvgpu_config cfg{};
+    Pipeline pl;
+    std::unique_ptr<Scheduler> sched;
+    std::unique_ptr<Carrier> carrier;
+    GlibcRand rng;
+    Workspace ws;
+    std::vector<std::vector<float>> tail;  // per channel: input samples from in_base on
+    std::vector<float> car_tail;
+    int64_t in_base = 0;
+    int64_t res_base = 0, res_cap = 0;
+    std::vector<std::vector<float>> fifo;  // per channel output FIFO (the reference's outbuf ring)
+    size_t fifo_rd = 0;
+    int num_res = 0;
+    DevBuf d_in, d_out, d_car, d_len;
+    std::vector<float> h_stage;
+    cudaStream_t st = nullptr;
+    static constexpr int kF = 64;
+    ~pvgpu_stream() { if (st) cudaStreamDestroy(st); }
+};
+
+static int stream_run_new(pvgpu_stream *s, long k0, int added) {
+    Pipeline &pl = s->pl;
+    Scheduler &sc = *s->sched;
+    const DevPlan &p = pl.p;
+    const int C = s->cfg.channels;
+    CU(cudaSetDevice(pl.device));
+    const int64_t len = (int64_t)s->tail[0].size();
+    const int64_t in_stride = std::max<int64_t>((len + 3) & ~(int64_t)3, 4);
+    CU(s->d_in.ensure(sizeof(float) * (size_t)C * in_stride));
+    for (int c = 0; c < C; ++c)
+        if (len) CU(cudaMemcpyAsync(s->d_in.as<float>() + c * in_stride, s->tail[c].data(), sizeof(float) * len, cudaMemcpyHostToDevice, s->st));
+    // per-row limits: [0..C) valid input end, [C..2C) output limit, [2C] carrier length
+    std::vector<int64_t> lim(2 * C + 1);
+    for (int c = 0; c < C; ++c) { lim[c] = s->in_base + len; lim[C + c] = INT64_MAX; }
+    lim[2 * C] = s->in_base + (int64_t)s->car_tail.size();
+    CU(s->d_len.ensure(sizeof(int64_t) * lim.size()));
+    CU(cudaMemcpyAsync(s->d_len.p, lim.data(), sizeof(int64_t) * lim.size(), cudaMemcpyHostToDevice, s->st));
+    int rc;
+    if ((rc = pl.upload_schedule(sc, s->st))) return rc;
+    const SliceRec &first = sc.recs()[k0 - sc.recs_base()];
+    const int64_t out_base = first.out_off;
+    const int64_t new_out = sc.total_out() - out_base;
+    const int64_t out_stride = std::max<int64_t>((new_out + 3) & ~(int64_t)3, 4);
+    CU(s->d_out.ensure(sizeof(float) * (size_t)C * out_stride));
+    if (halo_of(sc.recs(), sc.recs_base()) > s->ws.Fr - s->ws.F) return fail(PVGPU_ESTATE, "too many overlapping (dropped) slices; retrieve output more often");
+    // resampler input stream: keep [res_base, res_total) resident, grow preserving the contents
+    if (p.rs_active) {
+        const int64_t need = sc.res_total() - s->res_base + 8;
+        if (need > s->res_cap) {
+            const int64_t ncap = std::max<int64_t>(need * 2, 1 << 16);
+            DevBuf nb;
+            CU(nb.ensure(sizeof(float) * (size_t)C * ncap));
+            CU(cudaMemsetAsync(nb.p, 0, sizeof(float) * (size_t)C * ncap, s->st));
+            if (s->res_cap) CU(cudaMemcpy2DAsync(nb.p, sizeof(float) * ncap, s->ws.res.p, sizeof(float) * s->res_cap, sizeof(float) * s->res_cap, C, cudaMemcpyDeviceToDevice, s->st));
+            CU(cudaStreamSynchronize(s->st));
+            std::swap(s->ws.res.p, nb.p);
+            std::swap(s->ws.res.bytes, nb.bytes);
+            s->res_cap = ncap;
+        }
+    }
+    DevRows g{};
+    g.rows = C; g.channels = C;
+    g.in = s->d_in.as<float>(); g.in_stride = in_stride; g.in_base = s->in_base;
+    g.n_in = s->d_len.as<int64_t>(); g.n_out = s->d_len.as<int64_t>() + C;
+    g.out = s->d_out.as<float>(); g.out_stride = out_stride; g.out_base = out_base;
+    s->ws.bind(pl, g);
+    g.res_stride = s->res_cap; g.res_base = s->res_base;
+    g.aux_base = k0;
+    if (pl.d.whisper) {
+        const size_t n = (size_t)added * C * p.H;
+        std::vector<float> ph(n);
+        const float two_pi = 2 * M_PI;
+        for (size_t i = 0; i < n; ++i) ph[i] = two_pi * (float)s->rng.next() / (float)2147483647;
+        CU(pl.b_whisper.ensure(sizeof(float) * n));
+        CU(cudaMemcpyAsync(pl.b_whisper.p, ph.data(), sizeof(float) * n, cudaMemcpyHostToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));
+    }
+    if (pl.d.vocoder) {
+        const int64_t clen = (int64_t)s->car_tail.size();
+        CU(s->d_car.ensure(sizeof(float) * (size_t)std::max<int64_t>(clen, 1)));
+        if (clen) CU(cudaMemcpyAsync(s->d_car.p, s->car_tail.data(), sizeof(float) * clen, cudaMemcpyHostToDevice, s->st));
+        CU(pl.b_carmag.ensure(sizeof(float) * (size_t)added * p.Hp));
+        CU(pl.b_carph.ensure(sizeof(float) * (size_t)added * p.Hp));
+        DevRows gc{};
+        gc.rows = 1; gc.channels = 1;
+        gc.in = s->d_car.as<float>(); gc.in_stride = 0; gc.in_base = s->in_base; gc.n_in = s->d_len.as<int64_t>() + 2 * C;
+        gc.mag = pl.b_carmag.as<float>(); gc.phase = pl.b_carph.as<float>(); gc.F = added;
+        launch_analyse(p, gc, k0, added, s->st);
+    }
+    for (long k = k0; k < k0 + added; k += s->ws.F) pl.run_frames(g, k, (int)std::min<long>(s->ws.F, k0 + added - k), s->st);
+    CU(cudaGetLastError());
+    if (new_out > 0) {
+        s->h_stage.resize((size_t)C * new_out);
+        CU(cudaMemcpy2DAsync(s->h_stage.data(), sizeof(float) * new_out, s->d_out.p, sizeof(float) * out_stride, sizeof(float) * new_out, C, cudaMemcpyDeviceToHost, s->st));
+    }
+    CU(cudaStreamSynchronize(s->st));
+    for (int c = 0; c < C && new_out > 0; ++c) s->fifo[c].insert(s->fifo[c].end(), s->h_stage.begin() + (size_t)c * new_out, s->h_stage.begin() + (size_t)(c + 1) * new_out);
+    // forget what no later slice can need
+    const long k_next = k0 + added;
+    const int64_t new_base = (int64_t)k_next * p.hop;
+    const int64_t dropn = std::min<int64_t>(new_base - s->in_base, len);
+    for (int c = 0; c < C; ++c) s->tail[c].erase(s->tail[c].begin(), s->tail[c].begin() + dropn);
+    if (pl.d.vocoder) s->car_tail.erase(s->car_tail.begin(), s->car_tail.begin() + std::min<int64_t>(dropn, (int64_t)s->car_tail.size()));
+    s->in_base += dropn;
+    sc.trim(sc.recs().back().jlo, sc.ola_total());
+    if (p.rs_active) {
+        const int64_t L = p.rs_filt_len;
+        if (sc.res_total() - s->res_base > std::max<int64_t>(4 * L, s->res_cap / 2)) {
+            const int64_t keep_from = sc.res_total() - L;  // later taps start at res_off + last - L + 1 >= res_total - L + 1
+            CU(cudaMemcpy2DAsync(s->ws.res.p, sizeof(float) * s->res_cap, s->ws.res.as<float>() + (keep_from - s->res_base), sizeof(float) * s->res_cap,
+                                 sizeof(float) * L, C, cudaMemcpyDeviceToDevice, s->st));
+            CU(cudaStreamSynchronize(s->st));
+            s->res_base = keep_from;
+        }
+    }
+    return PVGPU_OK;
+}
+
+extern "C" {
+
+int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!out) return fail(PVGPU_EINVAL, "null out pointer");
+    std::unique_ptr<pvgpu_stream> s(new (std::nothrow) pvgpu_stream);
+    if (!s) return fail(PVGPU_ENOMEM, "out of host memory");
+    s->cfg = *cfg;
+    if ((rc = s->pl.init(*cfg))) return rc;
+    s->sched.reset(new Scheduler(s->pl.d, true));
+    if (s->pl.d.vocoder) s->carrier.reset(new Carrier(cfg->sample_rate, cfg->mode == PVGPU_VOCODER_CHORD));
+    s->tail.resize(cfg->channels);
+    s->fifo.resize(cfg->channels);
+    CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    const int halo = std::max(64, 4 * s->pl.d.N / std::max(1, s->pl.d.hop));
+    if ((rc = s->ws.ensure(s->pl, cfg->channels, pvgpu_stream::kF, halo, 0))) return rc;
+    if ((rc = s->ws.reset_state(s->pl, s->st))) return rc;
+    *out = s.release();
+    return PVGPU_OK;
+}
+
+void pvgpu_destroy(pvgpu_stream *s) {
+    if (!s) return;
+    cudaSetDevice(s->pl.device);
+    delete s;
+}
+
+int pvgpu_stream_info(const pvgpu_stream *s, pvgpu_info *info) {
+    if (!s || !info) return fail(PVGPU_EINVAL, "null argument");
+    fill_info(s->pl.d, info);
+    return PVGPU_OK;
+}
+
+int pvgpu_process(pvgpu_stream *s, const float *const *in, int n) {
+    if (!s || n < 0 || (n > 0 && !in)) return fail(PVGPU_EINVAL, "bad argument");
+    if (!s->pl.d.valid_mode) { s->num_res = 0; return PVGPU_OK; }  // phasevocoder.cc:104-106: unknown mode does nothing
+    const int C = s->cfg.channels;
+    for (int c = 0; c < C; ++c) s->tail[c].insert(s->tail[c].end(), in[c], in[c] + n);
+    if (s->carrier) {
+        const size_t at = s->car_tail.size();
+        s->car_tail.resize(at + n);
+        s->carrier->generate(s->car_tail.data() + at, (size_t)n);
+    }
+    const long k0 = s->sched->recs_base() + s->sched->slices();
+    const int added = s->sched->feed(n);
+    if (added > 0) {
+        int rc = stream_run_new(s, k0, added);
+        if (rc) return rc;
+    }
+    s->num_res = (int)s->sched->available();
+    return PVGPU_OK;
+}
+
+int pvgpu_available(const pvgpu_stream *s) { return s ? s->num_res : 0; }
+
+int pvgpu_retrieve(pvgpu_stream *s, float *const *out, int n) {
+    if (!s || n < 0 || (n > 0 && !out)) return -fail(PVGPU_EINVAL, "bad argument");
+    long k = std::min<long>(n, s->num_res);  // phasevocoder.cc:111-113
+    k = std::min<long>(k, s->sched->available());
+    for (int c = 0; c < s->cfg.channels; ++c) std::memcpy(out[c], s->fifo[c].data() + s->fifo_rd, sizeof(float) * (size_t)k);
+    s->fifo_rd += (size_t)k;
+    s->sched->drain(k);
+    if (s->fifo_rd > (1u << 20)) {
+        for (auto &f : s->fifo) f.erase(f.begin(), f.begin() + (long)s->fifo_rd);
+        s->fifo_rd = 0;
+    }
+    return (int)k;
+}
+
+int pvgpu_process_block(pvgpu_stream *s, float *const *buf, int n, int *ready) {
+    if (!s || !ready) return fail(PVGPU_EINVAL, "bad argument");
+    const int m = s->cfg.mode;
+    if (m == PVGPU_NORMAL_STRETCH || m < -1 || m > 7) { *ready = 1; return PVGPU_OK; }  // processBlock routes neither (phasevocoder.cc:133-146)
+    int rc = pvgpu_process(s, buf, n);
+    if (rc) return rc;
+    if (s->num_res >= n) {  // processBlockNormal, phasevocoder.cc:156-183
+        const int saved = s->num_res;
+        pvgpu_retrieve(s, buf, n);
+        s->num_res = saved;
+        *ready = 1;
+    } else {
+        *ready = 0;
+    }
+    return PVGPU_OK;
+}
+
+}  // extern "C"

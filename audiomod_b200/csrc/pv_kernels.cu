@@ -1,0 +1,562 @@
+// Hand-written sm_100a kernels of the batched phase vocoder.
+//
+// Stage map (reference file:line relative to the reference tree):
+//   k_analyse      frame gather + Hann + fftshift + KissFFT-order real FFT + polar
+//                  (phasevocoderprocess.cc:492-503, phasevocoderimpl.h:167-181, kiss_fftr.c:67-121,
+//                   kiss_fft.c:36-104,250-286, FFT.cc:2617-2631)
+//   k_phase_core   peak picking / peak linking / phase locking, and the classic per-bin propagation
+//                  (phasevocoderprocess.cc:574-706, 708-753)
+//   k_int_ratio    coremode 2 (phasevocoderprocess.cc:558-572)
+//   k_fixed_phase  robotic / whisper (phasevocoderprocess.cc:805-822)
+//   k_synthesise   [freq-comp warp :842-923] [vocoder band modulation :755-776] 1/N scale, polar->cartesian,
+//                  inverse real FFT (kiss_fftr.c:123-159), ifftshift + Hann (:1024-1056, impl.h:183-198)
+//   k_overlap_add  overlap-add in frame order + window-sum normalisation (:1057-1073, 1152, 1185-1190)
+//   k_resample     Speex quality-4 windowed-sinc resampler (speex/resample.c:352-403,462-560)
+//
+// Rounding discipline: everything that feeds a discrete decision of the reference (the forward FFT,
+// magnitude, atan2f, and the phase arithmetic) uses __f*_rn / __d*_rn intrinsics, which nvcc never
+// contracts into FMAs, in the reference's operation order.  The synthesis side (inverse FFT, OLA,
+// resampler) is held to the 1e-4 / 90 dB tolerance and may use FMA.
+#include "pv_kernels.cuh"
+#include "pv_math.cuh"
+
+namespace pvgpu {
+
+// ------------------------------------------------------------------------------------------------
+// complex helpers in the reference's operation order (_kiss_fft_guts.h:87-89, kiss_fft.c:36-104)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmul_rn(float2 a, float2 b) {
+    return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float2 cadd_rn(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 csub_rn(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+
+template <bool kInverse>
+__device__ __forceinline__ void bfly4(float2 &f0, float2 &f1, float2 &f2, float2 &f3, float2 t1, float2 t2, float2 t3) {
+    const float2 s0 = cmul_rn(f1, t1), s1 = cmul_rn(f2, t2), s2 = cmul_rn(f3, t3);
+    const float2 s5 = csub_rn(f0, s1);
+    f0 = cadd_rn(f0, s1);
+    const float2 s3 = cadd_rn(s0, s2), s4 = csub_rn(s0, s2);
+    f2 = csub_rn(f0, s3);
+    f0 = cadd_rn(f0, s3);
+    if (kInverse) {
+        f1 = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
+        f3 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+    } else {
+        f1 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+        f3 = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
+    }
+}
+
+// All butterfly stages of the nc-point complex FFT, in place in shared memory (data already permuted).
+template <bool kInverse>
+__device__ __forceinline__ void fft_stages(const DevPlan &p, float2 *F) {
+    const float2 *__restrict__ tw = kInverse ? p.tw_inv : p.tw_fwd;
+    const int nc = p.nc;
+    for (int s = 0; s < p.nstages; ++s) {
+        const int m = p.span[s], rad = p.radix[s];
+        const int fstride = nc / (m * rad);
+        if (rad == 2) {
+            for (int b = threadIdx.x; b < nc / 2; b += blockDim.x) {
+                const int grp = b / m, k = b - grp * m;
+                float2 *f = F + grp * 2 * m + k;
+                const float2 t = cmul_rn(f[m], __ldg(&tw[k * fstride]));
+                const float2 a = f[0];
+                f[m] = csub_rn(a, t);
+                f[0] = cadd_rn(a, t);
+            }
+        } else {
+            for (int b = threadIdx.x; b < nc / 4; b += blockDim.x) {
+                const int grp = b / m, k = b - grp * m;
+                float2 *f = F + grp * 4 * m + k;
+                float2 f0 = f[0], f1 = f[m], f2 = f[2 * m], f3 = f[3 * m];
+                bfly4<kInverse>(f0, f1, f2, f3, __ldg(&tw[k * fstride]), __ldg(&tw[2 * k * fstride]), __ldg(&tw[3 * k * fstride]));
+                f[0] = f0; f[m] = f1; f[2 * m] = f2; f[3 * m] = f3;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_analyse: one CTA per (frame, row)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_analyse(const DevPlan p, const DevRows g, long k0) {
+    extern __shared__ float smem[];
+    float *s_t = smem;                       // N floats: windowed, fft-shifted frame
+    float2 *s_f = (float2 *)(smem + p.N);    // nc complex
+    const int row = blockIdx.y;
+    const long k = k0 + blockIdx.x;
+    const int N = p.N, nc = p.nc, hs = N / 2;
+    const float *__restrict__ x = g.in + (int64_t)row * g.in_stride;
+    const int64_t start = (int64_t)k * p.hop;
+    const int64_t nvalid = g.n_in[row];
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const int64_t gi = start + j;
+        const float v = gi < nvalid ? x[gi - g.in_base] : 0.f;
+        s_t[(j + hs) & (N - 1)] = __fmul_rn(v, __ldg(&p.window[j]));
+    }
+    __syncthreads();
+    const float2 *s_tc = (const float2 *)s_t;
+    for (int o = threadIdx.x; o < nc; o += blockDim.x) s_f[o] = s_tc[p.perm[o]];
+    __syncthreads();
+    fft_stages<false>(p, s_f);
+    // real-FFT post-pass (kiss_fftr.c:67-121) + polar (FFT.cc:2617-2631)
+    float *__restrict__ mag = g.mag + ((int64_t)row * g.F + blockIdx.x) * p.Hp;
+    float *__restrict__ ph = g.phase + ((int64_t)row * g.F + blockIdx.x) * p.Hp;
+    for (int kk = threadIdx.x; kk <= nc / 2; kk += blockDim.x) {
+        if (kk == 0) {
+            const float tr = s_f[0].x, ti = s_f[0].y;
+            const float dc = __fadd_rn(tr, ti), ny = __fsub_rn(tr, ti);
+            mag[0] = __fsqrt_rn(__fadd_rn(__fmul_rn(dc, dc), 0.f));
+            ph[0] = pv_atan2f(0.f, dc);
+            mag[nc] = __fsqrt_rn(__fadd_rn(__fmul_rn(ny, ny), 0.f));
+            ph[nc] = pv_atan2f(0.f, ny);
+        } else {
+            const float2 fpk = s_f[kk];
+            const float2 fq = s_f[nc - kk];
+            const float2 fpnk = make_float2(fq.x, -fq.y);
+            const float2 f1k = cadd_rn(fpk, fpnk), f2k = csub_rn(fpk, fpnk);
+            const float2 tw = cmul_rn(f2k, __ldg(&p.stw_fwd[kk]));
+            const float ar = __fmul_rn(__fadd_rn(f1k.x, tw.x), 0.5f), ai = __fmul_rn(__fadd_rn(f1k.y, tw.y), 0.5f);
+            const float br = __fmul_rn(__fsub_rn(f1k.x, tw.x), 0.5f), bi = __fmul_rn(__fsub_rn(tw.y, f1k.y), 0.5f);
+            if (kk != nc - kk) {  // bin nc/2 is written twice by the reference; the second write wins
+                mag[kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
+                ph[kk] = pv_atan2f(ai, ar);
+            }
+            mag[nc - kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+            ph[nc - kk] = pv_atan2f(bi, br);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// phase core
+// ------------------------------------------------------------------------------------------------
+// princarg, src/common/system/sys.h:84-91 (double overload): mod(a + pi, -2pi) + pi with
+// mod(x, y) = x - y*floor(x/y)
+__device__ __forceinline__ double princarg_rn(double a) {
+    const double pi = 3.14159265358979323846, m2pi = -2.0 * 3.14159265358979323846;
+    const double x = __dadd_rn(a, pi);
+    const double q = floor(__ddiv_rn(x, m2pi));
+    return __dadd_rn(__dsub_rn(x, __dmul_rn(m2pi, q)), pi);
+}
+
+__device__ __forceinline__ float sub3_rn(float a, float b, float c) { return __fsub_rn(__fsub_rn(a, b), c); }
+
+// One CTA per stream; frames and channels are visited in the reference's order because the peak
+// lists are shared by the channels of a stream (phasevocoderimpl.h:237-238) and "first entry" is a
+// per-process flag (phasevocoderprocess.cc:602,716).
+template <bool kLocked>
+__global__ void k_phase_core(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base, long k0, int nframes) {
+    extern __shared__ float smem[];
+    const int half = p.half, C = g.channels, maxpk = g.maxpk;
+    float *s_mag = smem;                        // Hp
+    float *s_ph = s_mag + p.Hp;                 // Hp
+    float *s_pp = s_ph + p.Hp;                  // C * half   previous analysis phase
+    float *s_po = s_pp + C * half;              // C * half   previous output phase
+    int *s_cur = (int *)(s_po + C * half);      // maxpk
+    int *s_prev = s_cur + maxpk;                // maxpk
+    int *s_start = s_prev + maxpk;              // maxpk + 1
+    float *s_rot = (float *)(s_start + maxpk + 1);  // maxpk
+    int *s_misc = (int *)(s_rot + maxpk);       // [0]=npk [1]=nprev [2]=first, [8..8+32) warp sums
+    const int stream = blockIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+
+    for (int c = 0; c < C; ++c) {
+        const int64_t row = (int64_t)stream * C + c;
+        for (int i = tid; i < half; i += nthr) {
+            s_pp[c * half + i] = g.prev_phase[row * half + i];
+            s_po[c * half + i] = g.prev_out[row * half + i];
+        }
+    }
+    int *gpk = g.peaks + (int64_t)stream * (1 + maxpk);
+    if (tid == 0) { s_misc[1] = gpk[0]; s_misc[2] = g.first_flag[stream]; }
+    __syncthreads();
+    for (int i = tid; i < s_misc[1]; i += nthr) s_prev[i] = gpk[1 + i];
+    __syncthreads();
+
+    const int E = (half + nthr - 1) / nthr;  // contiguous bins per thread
+    for (int f = 0; f < nframes; ++f) {
+        const float phase_inc = (float)recs[k0 + f - recs_base].phase_inc;  // size_t -> float conversion of the reference
+        const float hopf = (float)p.hop;
+        for (int c = 0; c < C; ++c) {
+            const int64_t row = (int64_t)stream * C + c;
+            float *__restrict__ gph = g.phase + (row * g.F + f) * p.Hp;
+            const float *__restrict__ gmag = g.mag + (row * g.F + f) * p.Hp;
+            for (int i = tid; i < half; i += nthr) {
+                s_ph[i] = gph[i];
+                if (kLocked) s_mag[i] = gmag[i];
+            }
+            __syncthreads();
+            float *pp = s_pp + c * half, *po = s_po + c * half;
+            int npk = 0;
+            if (kLocked) {
+                // peak picking (:587-596): every strict +-2 local maximum with 2 <= b <= half-3, in order
+                int cnt = 0;
+                unsigned flags = 0;
+                const int b0 = tid * E;
+                for (int e = 0; e < E; ++e) {
+                    const int b = b0 + e;
+                    if (b >= 2 && b + 2 < half) {
+                        const float m = s_mag[b];
+                        if (m > s_mag[b - 1] && m > s_mag[b - 2] && m > s_mag[b + 1] && m > s_mag[b + 2]) { flags |= 1u << e; ++cnt; }
+                    }
+                }
+                int incl = cnt;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (lane == 31) s_misc[8 + warp] = incl;
+                __syncthreads();
+                int base = 0;
+                for (int w = 0; w < warp; ++w) base += s_misc[8 + w];
+                int pos = base + incl - cnt;
+                for (int e = 0; e < E; ++e)
+                    if (flags & (1u << e)) s_cur[pos++] = b0 + e;
+                if (tid == nthr - 1) s_misc[0] = base + incl;
+                __syncthreads();
+                npk = s_misc[0];
+            }
+            const int nprev = s_misc[1];
+            const int first = s_misc[2];
+            if (first) {
+                // first call of the process: pass the analysis phase through and seed the state (:606-616)
+                for (int i = tid; i < half; i += nthr) { const float tp = s_ph[i]; pp[i] = tp; po[i] = tp; }
+            } else if (npk == 0 || nprev == 0) {
+                // classic propagation (:617-636 / :731-748)
+                for (int i = tid; i < half; i += nthr) {
+                    const float omega = __ldg(&p.omega[i]);
+                    const float phi = s_ph[i];
+                    const float dphi = (float)__dadd_rn((double)omega, princarg_rn((double)sub3_rn(phi, pp[i], omega)));
+                    const float adv = __fdiv_rn(__fmul_rn(dphi, phase_inc), hopf);
+                    const float outp = (float)princarg_rn((double)__fadd_rn(po[i], adv));
+                    pp[i] = phi;
+                    po[i] = outp;
+                    gph[i] = outp;
+                }
+            } else {
+                // per-peak rotation (:641-667) and region start (:668-683)
+                for (int pk = tid; pk < npk; pk += nthr) {
+                    const int p2 = s_cur[pk];
+                    int lo = 0, hi = nprev;  // first previous peak >= p2
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prev[mid] < p2) lo = mid + 1; else hi = mid; }
+                    int j;
+                    if (lo == 0) j = 0;
+                    else if (lo == nprev) j = nprev - 1;
+                    else j = (s_prev[lo] - p2 < p2 - s_prev[lo - 1]) ? lo : lo - 1;  // ties keep the lower index (:644-652)
+                    const int p1 = s_prev[j];
+                    const float avg_p = (float)((double)(p1 + p2) * 0.5);
+                    const float pomega = (float)__ddiv_rn(__dmul_rn(p.two_pi_hop, (double)__fsub_rn(avg_p, 1.0f)), (double)p.N);
+                    const float dphi = (float)__dadd_rn((double)pomega, princarg_rn((double)sub3_rn(s_ph[p2], pp[p1], pomega)));
+                    const float target = (float)princarg_rn((double)__fadd_rn(po[p1], __fdiv_rn(__fmul_rn(dphi, phase_inc), hopf)));
+                    s_rot[pk] = (float)princarg_rn((double)__fsub_rn(target, s_ph[p2]));
+                    s_start[pk] = pk == 0 ? 0 : (s_cur[pk - 1] + p2 + 1) >> 1;  // round((a+b)*0.5), half away from zero
+                }
+                if (tid == 0) s_start[npk] = half;
+                __syncthreads();
+                // lock every bin to its region's peak rotation (:685-699)
+                const int b0 = tid * E;
+                if (b0 < half) {
+                    int lo = 0, hi = npk;  // last pk with start <= b0
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_start[mid] <= b0) lo = mid; else hi = mid; }
+                    int pk = lo;
+                    for (int e = 0; e < E; ++e) {
+                        const int i = b0 + e;
+                        if (i >= half) break;
+                        while (s_start[pk + 1] <= i) ++pk;
+                        const float phi = s_ph[i];
+                        const float locked = (float)princarg_rn((double)__fadd_rn(phi, s_rot[pk]));
+                        pp[i] = phi;
+                        po[i] = locked;
+                        gph[i] = locked;
+                    }
+                }
+            }
+            __syncthreads();
+            if (kLocked) {
+                for (int i = tid; i < npk; i += nthr) s_prev[i] = s_cur[i];
+                if (tid == 0) s_misc[1] = npk;
+            }
+            if (tid == 0) s_misc[2] = 0;
+            __syncthreads();
+        }
+    }
+    for (int c = 0; c < C; ++c) {
+        const int64_t row = (int64_t)stream * C + c;
+        for (int i = tid; i < half; i += nthr) {
+            g.prev_phase[row * half + i] = s_pp[c * half + i];
+            g.prev_out[row * half + i] = s_po[c * half + i];
+        }
+    }
+    const int nprev = s_misc[1];
+    for (int i = tid; i < nprev; i += nthr) gpk[1 + i] = s_prev[i];
+    if (tid == 0) { gpk[0] = nprev; g.first_flag[stream] = s_misc[2]; }
+}
+
+// coremode 2: phase *= phaseIncrement / hop (two float roundings, :558-572)
+__global__ void k_int_ratio(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base, long k0) {
+    const int row = blockIdx.y, f = blockIdx.x;
+    float *__restrict__ gph = g.phase + ((int64_t)row * g.F + f) * p.Hp;
+    const float phase_inc = (float)recs[k0 + f - recs_base].phase_inc, hopf = (float)p.hop;
+    for (int i = threadIdx.x; i < p.half; i += blockDim.x) gph[i] = __fdiv_rn(__fmul_rn(gph[i], phase_inc), hopf);
+}
+
+// robotic (zeros) / whisper (table of 2*pi*rand()/RAND_MAX drawn slice-major, channel, bin): all H bins
+__global__ void k_fixed_phase(const DevPlan p, const DevRows g, const float *__restrict__ table, long k0) {
+    const int row = blockIdx.y, f = blockIdx.x;
+    const int c = row % g.channels;
+    float *__restrict__ gph = g.phase + ((int64_t)row * g.F + f) * p.Hp;
+    const float *__restrict__ t = table ? table + ((int64_t)(k0 + f - g.aux_base) * g.channels + c) * p.H : nullptr;
+    for (int i = threadIdx.x; i < p.H; i += blockDim.x) gph[i] = t ? t[i] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_synthesise: one CTA per (frame, row)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_synthesise(const DevPlan p, const DevRows g, const float *__restrict__ car_mag, const float *__restrict__ car_phase, long k0) {
+    extern __shared__ float smem[];
+    const int N = p.N, nc = p.nc, H = p.H, hs = N / 2;
+    float *b0 = smem;                             // 2H floats: mag | phase, later nc complex (pre-pass output)
+    float2 *b1 = (float2 *)(smem + 2 * H + 2);    // H complex: packed spectrum, later the FFT workspace
+    const int row = blockIdx.y, f = blockIdx.x;
+    const long k = k0 + f;
+    const float *__restrict__ gmag = g.mag + ((int64_t)row * g.F + f) * p.Hp;
+    const float *__restrict__ gph = g.phase + ((int64_t)row * g.F + f) * p.Hp;
+    float *s_mag = b0, *s_ph = b0 + H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { s_mag[i] = gmag[i]; s_ph[i] = gph[i]; }
+    __syncthreads();
+    const bool vocoder = car_mag != nullptr;
+    const int band_len = N / 1024;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        float m, ph;
+        if (vocoder) {
+            // modifySliceVocoder (:755-776): carrier magnitude scaled by the band mean of the input
+            m = car_mag[(int64_t)(k - g.aux_base) * p.Hp + i];
+            ph = car_phase[(int64_t)(k - g.aux_base) * p.Hp + i];
+            if (i == 0 || i == H - 1) {
+                m = 0.f;
+            } else if (band_len > 0) {
+                const int bs = (i / band_len) * band_len;
+                float mean = 0.f;
+                for (int e = 0; e < band_len; ++e) mean = __fadd_rn(mean, s_mag[bs + e]);
+                mean = __fdiv_rn(mean, (float)(band_len * 2));
+                m = __fmul_rn(m, mean);
+            }
+        } else if (p.freq_comp != 0.f) {
+            // freqCompSlice (:842-923): both in-place loop orders read only not-yet-overwritten sources,
+            // so the warp is a gather from the unmodified spectrum
+            if (p.freq_comp > 1.0f || i < hs) {
+                const int src = __float2int_rn(__fmul_rn((float)i, p.freq_comp));
+                if (src > hs) {
+                    m = 0.f; ph = 0.f;
+                } else {
+                    const float dw = (float)__ddiv_rn(__dmul_rn(p.two_pi_hop, (double)(i - src)), (double)N);
+                    m = s_mag[src];
+                    ph = __fadd_rn(s_ph[src], dw);
+                }
+            } else {  // expand direction leaves the Nyquist bin alone
+                m = s_mag[i]; ph = s_ph[i];
+            }
+            m = __fmul_rn(m, p.fixed_gain);
+        } else {
+            m = s_mag[i]; ph = s_ph[i];
+        }
+        m = __fmul_rn(m, p.inv_n);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        b1[i] = make_float2(m * cs, m * sn);
+    }
+    __syncthreads();
+    // inverse real-FFT pre-pass (kiss_fftr.c:123-159)
+    float2 *tmp = (float2 *)b0;
+    for (int kk = threadIdx.x; kk <= nc / 2; kk += blockDim.x) {
+        if (kk == 0) {
+            tmp[0] = make_float2(b1[0].x + b1[nc].x, b1[0].x - b1[nc].x);
+        } else {
+            const float2 fk = b1[kk];
+            const float2 fq = b1[nc - kk];
+            const float2 fnkc = make_float2(fq.x, -fq.y);
+            const float2 fek = cadd_rn(fk, fnkc), t = csub_rn(fk, fnkc);
+            const float2 fok = cmul_rn(t, __ldg(&p.stw_inv[kk]));
+            const float2 a = cadd_rn(fek, fok);
+            const float2 b = csub_rn(fek, fok);
+            if (kk != nc - kk) tmp[kk] = a;
+            tmp[nc - kk] = make_float2(b.x, -b.y);
+        }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < nc; o += blockDim.x) b1[o] = tmp[p.perm[o]];
+    __syncthreads();
+    fft_stages<true>(p, b1);
+    // ifftshift + synthesis window (impl.h:183-198, :1052-1056)
+    const float *time = (const float *)b1;
+    float *__restrict__ out = g.frames + ((int64_t)row * g.Fr + (k % g.Fr)) * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) out[i] = time[(i + hs) & (N - 1)] * __ldg(&p.window[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_overlap_add: one CTA per (slice, row).  The accumulator of the reference receives frames in slice
+// order starting from zero, so summing the covering frames in slice order is the same float sequence.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_overlap_add(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
+                              int64_t norm_base, long recs_base, long k0) {
+    const int row = blockIdx.y;
+    const long k = k0 + blockIdx.x;
+    const SliceRec r = recs[k - recs_base];
+    if (r.flags & 1) return;  // dropped slice: accumulated (by later gathers), nothing written
+    const int N = p.N;
+    const float *__restrict__ fr = g.frames + (int64_t)row * g.Fr * N;
+    for (int i = threadIdx.x; i < r.shift_inc; i += blockDim.x) {
+        const int64_t t = r.ola_off + i;
+        float acc = 0.f;
+        for (long j = r.jlo; j <= k; ++j) {
+            const int64_t off = t - recs[j - recs_base].ola_off;
+            if (off < N) acc += fr[(j % g.Fr) * N + off];
+        }
+        const float v = acc / norm[t - norm_base];
+        if (p.rs_active) {
+            if (i < r.consumed) g.res[(int64_t)row * g.res_stride + (r.res_off + i - g.res_base)] = v;
+        } else if (i < r.n_write && r.out_off + i < g.n_out[row]) {
+            g.out[(int64_t)row * g.out_stride + (r.out_off + i - g.out_base)] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_resample: one CTA per (slice, row); one thread per output sample
+// ------------------------------------------------------------------------------------------------
+__global__ void k_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base, long k0) {
+    const int row = blockIdx.y;
+    const long k = k0 + blockIdx.x;
+    const SliceRec r = recs[k - recs_base];
+    if (r.flags & 1) return;
+    const int L = (int)p.rs_filt_len;
+    const float *__restrict__ x = g.res + (int64_t)row * g.res_stride;
+    const float *__restrict__ tab = p.rs_table;
+    int n_store = r.n_write;
+    if (r.out_off + n_store > g.n_out[row]) n_store = (int)max((int64_t)0, g.n_out[row] - r.out_off);
+    for (int i = threadIdx.x; i < n_store; i += blockDim.x) {
+        // position of output i: i steps of (int_advance, frac_advance) with carry (resample.c:548-554)
+        const uint64_t fr = (uint64_t)r.rs_frac + (uint64_t)i * (uint64_t)p.rs_frac_adv;
+        const int last = r.rs_last + i * p.rs_int_adv + (int)(fr / p.rs_den);
+        const uint32_t frac_num = (uint32_t)(fr % p.rs_den);
+        const int64_t pos0 = r.res_off + last - L + 1;  // global resampler-input position of tap 0
+        float sum;
+        if (p.rs_direct) {
+            sum = 0.f;
+            const float *t = tab + (size_t)frac_num * L;
+            for (int j = 0; j < L; ++j) {
+                const int64_t q = pos0 + j;
+                const float v = q >= 0 ? x[q - g.res_base] : 0.f;
+                sum += v * t[j];
+            }
+        } else {
+            const uint32_t ov = p.rs_oversample;
+            const int offset = (int)(frac_num * ov / p.rs_den);
+            const float frac = ((float)((frac_num * ov) % p.rs_den)) / p.rs_den;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int j = 0; j < L; ++j) {
+                const int64_t q = pos0 + j;
+                const float v = q >= 0 ? x[q - g.res_base] : 0.f;
+                const float *t = tab + 4 + (j + 1) * (int)ov - offset;
+                a0 += v * t[-2];
+                a1 += v * t[-1];
+                a2 += v * t[0];
+                a3 += v * t[1];
+            }
+            // cubic_coef (resample.c:339-351)
+            const float i0 = -0.16667f * frac + 0.16667f * frac * frac * frac;
+            const float i1 = frac + 0.5f * frac * frac - 0.5f * frac * frac * frac;
+            const float i3 = -0.33333f * frac + 0.5f * frac * frac - 0.16667f * frac * frac * frac;
+            const float i2 = (float)(1. - i0 - i1 - i3);
+            sum = (i0 * a0) + (i1 * a1) + (i2 * a2) + (i3 * a3);
+        }
+        g.out[(int64_t)row * g.out_stride + (r.out_off + i - g.out_base)] = sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static int fft_threads(const DevPlan &p) {
+    int t = p.nc / 4;
+    if (t < 64) t = 64;
+    if (t > 1024) t = 1024;
+    return t;
+}
+
+size_t smem_analyse(const DevPlan &p) { return sizeof(float) * 2 * (size_t)p.N; }
+size_t smem_synthesise(const DevPlan &p) { return sizeof(float) * ((size_t)2 * p.H + 2 + (size_t)2 * p.H + 2); }
+size_t smem_phase_core(const DevPlan &p, int channels, int maxpk) {
+    return sizeof(float) * ((size_t)2 * p.Hp + (size_t)2 * channels * p.half + (size_t)4 * maxpk + 1 + 8 + 32 + 8);
+}
+
+cudaError_t configure_kernels() {
+    cudaError_t e;
+    const int big = 200 * 1024;
+    if ((e = cudaFuncSetAttribute(k_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_synthesise, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_phase_core<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_phase_core<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+void launch_analyse(const DevPlan &p, const DevRows &g, long k0, int nframes, cudaStream_t st) {
+    dim3 grid(nframes, g.rows);
+    k_analyse<<<grid, fft_threads(p), smem_analyse(p), st>>>(p, g, k0);
+}
+
+void launch_phase_core(const DevPlan &p, const DevRows &g, int coremode, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
+    if (coremode == 2) {
+        dim3 grid(nframes, g.rows);
+        k_int_ratio<<<grid, 256, 0, st>>>(p, g, recs, recs_base, k0);
+        return;
+    }
+    const int streams = g.rows / g.channels;
+    const size_t sm = smem_phase_core(p, g.channels, g.maxpk);
+    int threads = p.half / 4;
+    if (threads < 64) threads = 64;
+    if (threads > 512) threads = 512;
+    if (coremode == 1) k_phase_core<true><<<streams, threads, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+    else k_phase_core<false><<<streams, threads, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+}
+
+void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table, long k0, int nframes, cudaStream_t st) {
+    dim3 grid(nframes, g.rows);
+    k_fixed_phase<<<grid, 256, 0, st>>>(p, g, table, k0);
+}
+
+void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase, long k0, int nframes, cudaStream_t st) {
+    dim3 grid(nframes, g.rows);
+    k_synthesise<<<grid, fft_threads(p), smem_synthesise(p), st>>>(p, g, car_mag, car_phase, k0);
+}
+
+void launch_overlap_add(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
+                        long k0, int nframes, cudaStream_t st) {
+    dim3 grid(nframes, g.rows);
+    k_overlap_add<<<grid, 128, 0, st>>>(p, g, recs, norm, norm_base, recs_base, k0);
+}
+
+void launch_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
+    dim3 grid(nframes, g.rows);
+    k_resample<<<grid, 128, 0, st>>>(p, g, recs, recs_base, k0);
+}
+
+}  // namespace pvgpu
+
+// ------------------------------------------------------------------------------------------------
+// unit-test kernels (pvgpu_test_* in include/pvgpu.h)
+// ------------------------------------------------------------------------------------------------
+namespace pvgpu {
+__global__ void k_test_atan2f(int64_t n, const float *__restrict__ y, const float *__restrict__ x, float *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = pv_atan2f(y[i], x[i]);
+}
+__global__ void k_test_princarg(int64_t n, const double *__restrict__ a, double *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = princarg_rn(a[i]);
+}
+void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st) { k_test_atan2f<<<592, 256, 0, st>>>(n, y, x, out); }
+void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st) { k_test_princarg<<<592, 256, 0, st>>>(n, a, out); }
+}  // namespace pvgpu

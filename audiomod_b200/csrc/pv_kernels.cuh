@@ -1,0 +1,78 @@
+// Device-side view of a batch and the kernel launchers (sm_100a).  See pv_kernels.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "pv_plan.h"
+
+namespace pvgpu {
+
+constexpr int kMaxStages = 8;
+
+// Constant tables + sizes, passed by value to every kernel.
+struct DevPlan {
+    int N, H, half, nc, hop, Hp;        // Hp: padded row length of a spectrum (floats)
+    int nstages;
+    int radix[kMaxStages], span[kMaxStages];
+    const float *window;                // N
+    const float2 *tw_fwd, *tw_inv;      // nc
+    const float2 *stw_fwd, *stw_inv;    // nc
+    const uint16_t *perm;               // nc
+    const float *omega;                 // half
+    float inv_n;                        // 1.f / N
+    double two_pi_hop;                  // 2*M_PI*hop  (double product, phasevocoderprocess.cc:625)
+    // frequency-axis warp (formant / gender), 0 = off
+    float freq_comp, fixed_gain;
+    // resampler
+    int rs_active, rs_direct;
+    uint32_t rs_num, rs_den, rs_filt_len, rs_oversample;
+    int rs_int_adv, rs_frac_adv;
+    const float *rs_table;
+    int rs_table_len;
+};
+
+// One group of channel rows being processed; all pointers are device pointers.
+struct DevRows {
+    int rows;                 // channel rows in this group (streams * channels)
+    int channels;
+    const float *in;          // [rows][in_stride], element 0 is input sample in_base
+    int64_t in_stride, in_base;
+    const int64_t *n_in;      // per row: valid input samples (zeros beyond), global coordinates
+    float *mag, *phase;       // [rows][F][Hp] spectra of the current frame chunk
+    int F;                    // frame slots per row in mag/phase
+    float *frames;            // [rows][Fr][N] synthesised frames, slot = frame % Fr
+    int Fr;
+    float *res;               // [rows][res_stride] resampler input stream, element 0 is position res_base
+    int64_t res_stride, res_base;
+    float *out;               // [rows][out_stride], element 0 is output position out_base
+    int64_t out_stride, out_base;
+    const int64_t *n_out;     // per row: output positions >= n_out are not stored (truncation to the stream's length)
+    float *prev_phase, *prev_out;   // [rows][half] phase-core state
+    int *peaks;               // [streams][1 + maxpk]: count, then previous peak list (shared by a stream's channels)
+    int maxpk;
+    int *first_flag;          // [streams] 1 until the first slice of the stream went through the core
+    long aux_base;            // slice index of element 0 of the whisper table / carrier spectra
+};
+
+void launch_analyse(const DevPlan &p, const DevRows &g, long k0, int nframes, cudaStream_t st);
+void launch_phase_core(const DevPlan &p, const DevRows &g, int coremode, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st);
+void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table /*[slices][channels][H] indexed by absolute slice, or null = zeros*/,
+                        long k0, int nframes, cudaStream_t st);
+void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase /*[slices][Hp] indexed by absolute slice, or null*/,
+                       long k0, int nframes, cudaStream_t st);
+void launch_overlap_add(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base,
+                        long recs_base, long k0, int nframes, cudaStream_t st);
+void launch_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st);
+
+void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
+void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
+
+// bytes of dynamic shared memory each kernel needs for this plan (for tests / occupancy notes)
+size_t smem_analyse(const DevPlan &p);
+size_t smem_phase_core(const DevPlan &p, int channels, int maxpk);
+size_t smem_synthesise(const DevPlan &p);
+
+// one-time opt-in for > 48 KB dynamic shared memory
+cudaError_t configure_kernels();
+
+}  // namespace pvgpu

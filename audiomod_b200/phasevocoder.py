@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference's phase-vocoder interface over the C ABI.
+
+`phasevocoder` mirrors audiomod::phasevocoder (include/dafx/phasevocoder.h:54-80 of the reference:
+same constructor arguments, processInData / getOutSamples / getOutData of modbase_offline and
+processBlock / outputReady of modbase, include/dafx/modbase.h:43-114).  `PhaseVocoderBatch` is the
+throughput entry point: many independent streams, each processed exactly like one fresh
+`audiomod-exe` run (main/main.cc:149,471-509).  All arithmetic happens in libpvgpu.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, Info, check
+
+# mode / coremode constants, include/dafx/phasevocoder.h:22-36
+CONSTANT, NORMAL_SHIFT, GENDER_CHANGE, FORMANT_PRESERVE = -1, 0, 1, 2
+VOCODER_ROSENBERG, VOCODER_CHORD, NORMAL_STRETCH, ROBOTIC, WHISPER = 3, 4, 5, 6, 7
+NORMAL_PV, PHASE_LOCKED, INT_RATIO = 0, 1, 2
+
+_fp = C.POINTER(C.c_float)
+
+
+def _cfg(sampleRate, numChannels, timeratio, pitchshift, mode, coremode, fftsize, hopsize, device) -> Config:
+    return Config(int(sampleRate), int(numChannels), float(timeratio), float(pitchshift), int(mode), int(coremode),
+                  int(fftsize), int(hopsize), int(device))
+
+
+def _info_dict(info: Info) -> dict:
+    return {k: getattr(info, k) for k, _ in Info._fields_}
+
+
+def describe(sampleRate, numChannels, timeratio, pitchshift, mode=NORMAL_SHIFT, coremode=PHASE_LOCKED, fftsize=2048,
+             hopsize=0) -> dict:
+    """Sizes the reference derives in Impl::calculateSizes (needs no GPU)."""
+    info = Info()
+    check(_lib.lib().pvgpu_describe(C.byref(_cfg(sampleRate, numChannels, timeratio, pitchshift, mode, coremode, fftsize,
+                                                  hopsize, 0)), C.byref(info)))
+    return _info_dict(info)
+
+
+def plan_counts(n_in, sampleRate, numChannels, timeratio, pitchshift, mode=NORMAL_SHIFT, coremode=PHASE_LOCKED, fftsize=2048,
+                hopsize=0, block=0) -> dict:
+    """Host-only dry run of one stream through the CLI block protocol: output length, slices, dropped slices."""
+    v = [C.c_int64() for _ in range(3)]
+    check(_lib.lib().pvgpu_plan_counts(C.byref(_cfg(sampleRate, numChannels, timeratio, pitchshift, mode, coremode, fftsize,
+                                                     hopsize, 0)), int(n_in), int(block), *[C.byref(x) for x in v]))
+    return dict(n_out=v[0].value, n_slices=v[1].value, n_dropped=v[2].value)
+
+
+def _chan_ptrs(a: np.ndarray):
+    arr = (_fp * a.shape[0])()
+    for c in range(a.shape[0]):
+        arr[c] = a[c].ctypes.data_as(_fp)
+    return arr
+
+
+class phasevocoder:
+    """One stream.  Buffers are planar float32 arrays of shape [numChannels, n]."""
+
+    def __init__(self, sampleRate, numChannels, timeratio, pitchshift, mode=NORMAL_SHIFT, coremode=PHASE_LOCKED,
+                 fftsize=2048, hopsize=0, device=0):
+        self._h = C.c_void_p()
+        self.num_channels_ = int(numChannels)
+        self._ready = False
+        check(_lib.lib().pvgpu_create(C.byref(_cfg(sampleRate, numChannels, timeratio, pitchshift, mode, coremode, fftsize,
+                                                    hopsize, device)), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().pvgpu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def setParams(self, params):  # empty in the reference (phasevocoder.h:62-72)
+        pass
+
+    def getParams(self, params):
+        pass
+
+    def processInData(self, inData: np.ndarray, num_in_samples: int | None = None) -> None:
+        x = np.ascontiguousarray(inData, dtype=np.float32)
+        n = x.shape[1] if num_in_samples is None else int(num_in_samples)
+        check(_lib.lib().pvgpu_process(self._h, _chan_ptrs(x), n))
+
+    def getOutSamples(self) -> int:
+        return _lib.lib().pvgpu_available(self._h)
+
+    def getOutData(self, num_out_samples: int) -> np.ndarray:
+        out = np.zeros((self.num_channels_, max(int(num_out_samples), 1)), dtype=np.float32)
+        k = _lib.lib().pvgpu_retrieve(self._h, _chan_ptrs(out), int(num_out_samples))
+        if k < 0:
+            check(-k)
+        self._ready = True
+        return out[:, :k]
+
+    def processBlock(self, bufferData: np.ndarray, num_samples: int | None = None) -> None:
+        """In place on a C-contiguous float32 [numChannels, n] array."""
+        assert bufferData.dtype == np.float32 and bufferData.flags.c_contiguous
+        n = bufferData.shape[1] if num_samples is None else int(num_samples)
+        ready = C.c_int(0)
+        check(_lib.lib().pvgpu_process_block(self._h, _chan_ptrs(bufferData), n, C.byref(ready)))
+        self._ready = bool(ready.value)
+
+    def outputReady(self) -> bool:
+        return self._ready
+
+    def info(self) -> dict:
+        info = Info()
+        check(_lib.lib().pvgpu_stream_info(self._h, C.byref(info)))
+        return _info_dict(info)
+
+
+class PhaseVocoderBatch:
+    """n_streams independent streams with one configuration (rows are channel-planar)."""
+
+    def __init__(self, n_streams, max_in_samples, sampleRate, numChannels, timeratio, pitchshift, mode=NORMAL_SHIFT,
+                 coremode=PHASE_LOCKED, fftsize=2048, hopsize=0, device=0):
+        self._h = C.c_void_p()
+        self.n_streams, self.channels = int(n_streams), int(numChannels)
+        self.n_in = self.n_out = None
+        check(_lib.lib().pvgpu_batch_create(C.byref(_cfg(sampleRate, numChannels, timeratio, pitchshift, mode, coremode,
+                                                          fftsize, hopsize, device)), self.n_streams, int(max_in_samples),
+                                            C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().pvgpu_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def info(self) -> dict:
+        info = Info()
+        check(_lib.lib().pvgpu_batch_info(self._h, C.byref(info)))
+        return _info_dict(info)
+
+    def tune(self, frames_per_chunk=0, rows_per_group=0):
+        check(_lib.lib().pvgpu_batch_tune(self._h, int(frames_per_chunk), int(rows_per_group)))
+
+    def plan(self, n_in, block: int = 0) -> np.ndarray:
+        n_in = np.ascontiguousarray(np.broadcast_to(np.asarray(n_in, dtype=np.int64), (self.n_streams,)))
+        n_out = np.zeros(self.n_streams, dtype=np.int64)
+        p = C.POINTER(C.c_int64)
+        check(_lib.lib().pvgpu_batch_plan(self._h, n_in.ctypes.data_as(p), int(block), n_out.ctypes.data_as(p)))
+        self.n_in, self.n_out = n_in, n_out
+        return n_out
+
+    def run_device(self, d_in_ptr: int, in_stride: int, d_out_ptr: int, out_stride: int, cuda_stream: int = 0, fmt=_lib.F32):
+        check(_lib.lib().pvgpu_batch_run_device(self._h, C.c_void_p(d_in_ptr), int(in_stride), C.c_void_p(d_out_ptr),
+                                                int(out_stride), fmt, C.c_void_p(cuda_stream)))
+
+    def run_host_rows(self, in_rows, out_rows, fmt=_lib.F32):
+        """in_rows / out_rows: lists of numpy arrays (or raw addresses), one per channel row."""
+        n = self.n_streams * self.channels
+        ip, op = (C.c_void_p * n)(), (C.c_void_p * n)()
+        for r in range(n):
+            ip[r] = in_rows[r] if isinstance(in_rows[r], int) else in_rows[r].ctypes.data
+            op[r] = out_rows[r] if isinstance(out_rows[r], int) else out_rows[r].ctypes.data
+        check(_lib.lib().pvgpu_batch_run_host(self._h, ip, op, fmt))
+
+    def run(self, streams):
+        """streams: list of float32 arrays [channels, n_i].  Plans for these lengths and returns the outputs."""
+        xs = [np.ascontiguousarray(x, dtype=np.float32) for x in streams]
+        assert len(xs) == self.n_streams and all(x.shape[0] == self.channels for x in xs)
+        n_out = self.plan([x.shape[1] for x in xs])
+        outs = [np.zeros((self.channels, int(n_out[s])), dtype=np.float32) for s in range(self.n_streams)]
+        in_rows = [xs[s][c] for s in range(self.n_streams) for c in range(self.channels)]
+        out_rows = [outs[s][c] for s in range(self.n_streams) for c in range(self.channels)]
+        self.run_host_rows(in_rows, out_rows)
+        return outs
+
+    def stats(self) -> dict:
+        v = [C.c_int64() for _ in range(4)]
+        check(_lib.lib().pvgpu_batch_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(kernel_launches=v[0].value, slices=v[1].value, h2d_bytes=v[2].value, d2h_bytes=v[3].value)

@@ -1,0 +1,133 @@
+/*
+ * pvgpu.h -- C ABI of the B200-native phase vocoder (libpvgpu.so).
+ *
+ * This is the drop-in boundary for the phase-vocoder path of tangkk/audiomod.  Nothing like it
+ * exists in the reference (it is a single-threaded C++ library); each entry point below names the
+ * reference interface it stands in for (file:line relative to the reference tree).  The C++ class
+ * audiomod::phasevocoder in audiomod_b200/csrc/pv_dropin.hpp and the Python mirror in
+ * audiomod_b200/phasevocoder.py are thin shims over these calls.
+ *
+ * Conventions: planar float32, one pointer per channel, caller-owned buffers valid only during the
+ * call (include/dafx/modbase.h:43,89,97).  Every function returns PVGPU_OK (0) or a PVGPU_E* code and
+ * never aborts (the reference aborts / throws, FFT.cc:3168,3220, memallocators.h:91);
+ * pvgpu_last_error() gives the message for the calling thread.  All computation runs on the GPU;
+ * there is no CPU fallback: without a usable CUDA device every create call fails with PVGPU_ECUDA.
+ */
+#ifndef PVGPU_H_
+#define PVGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { PVGPU_OK = 0, PVGPU_EINVAL = 1, PVGPU_ECUDA = 2, PVGPU_ENOMEM = 3, PVGPU_ESTATE = 4 };
+
+/* mode / coremode values: include/dafx/phasevocoder.h:22-36 */
+enum { PVGPU_CONSTANT = -1, PVGPU_NORMAL_SHIFT = 0, PVGPU_GENDER_CHANGE = 1, PVGPU_FORMANT_PRESERVE = 2,
+       PVGPU_VOCODER_ROSENBERG = 3, PVGPU_VOCODER_CHORD = 4, PVGPU_NORMAL_STRETCH = 5, PVGPU_ROBOTIC = 6, PVGPU_WHISPER = 7 };
+enum { PVGPU_NORMAL_PV = 0, PVGPU_PHASE_LOCKED = 1, PVGPU_INT_RATIO = 2 };
+
+/* sample formats of the batch entry points */
+enum { PVGPU_F32 = 0, PVGPU_S16 = 1 };
+
+/* Constructor arguments of audiomod::phasevocoder (include/dafx/phasevocoder.h:54,
+ * src/phasevocoder/phasevocoder.cc:24-60), plus the CUDA device ordinal. */
+typedef struct pvgpu_config {
+    int sample_rate;
+    int channels;
+    float time_ratio;        /* timeratio */
+    float pitch_semitones;   /* pitchshift, in semitones */
+    int mode;                /* PVGPU_NORMAL_SHIFT ... */
+    int coremode;            /* PVGPU_PHASE_LOCKED ... */
+    int fftsize;             /* rounded up to a power of two like the reference (phasevocoderimpl.cc:177-181) */
+    int hopsize;             /* 0 = automatic (phasevocoderimpl.cc:209-226) */
+    int device;              /* CUDA device ordinal */
+} pvgpu_config;
+
+/* Sizes the reference derives in Impl::calculateSizes (phasevocoderimpl.cc:169-263). */
+typedef struct pvgpu_info {
+    int fftsize, hop, bins;
+    float pitch_scale, hs_ratio;
+    int resampler_active, resampler_filt_len;
+    uint32_t resampler_num, resampler_den;
+    int64_t outbuf_capacity;
+} pvgpu_info;
+
+const char *pvgpu_last_error(void);
+int pvgpu_version(void);
+/* number of CUDA devices visible (0 when there is no driver/GPU) */
+int pvgpu_device_count(void);
+/* derived sizes only; needs no GPU */
+int pvgpu_describe(const pvgpu_config *cfg, pvgpu_info *info);
+/* Host-only dry run of one stream through the CLI block protocol (main/main.cc:149,471-509): how many samples come
+ * out, how many slices run, how many would be dropped because the output ring is full (phasevocoderprocess.cc:337-364).
+ * block = 0 uses max(480, sr/100).  Needs no GPU. */
+int pvgpu_plan_counts(const pvgpu_config *cfg, int64_t n_in, int block, int64_t *n_out, int64_t *n_slices, int64_t *n_dropped);
+
+/* ---------------------------------------------------------------------------------------------
+ * Streaming instance == one audiomod::phasevocoder object with fresh-process semantics.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pvgpu_stream pvgpu_stream;
+
+/* phasevocoder::phasevocoder + init (phasevocoder.cc:24-85) */
+int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out);
+/* phasevocoder::~phasevocoder (phasevocoder.cc:62-67) */
+void pvgpu_destroy(pvgpu_stream *s);
+/* modbase_offline::processInData (modbase.h:89, phasevocoder.cc:87-108): consume n samples per channel */
+int pvgpu_process(pvgpu_stream *s, const float *const *in, int n);
+/* modbase_offline::getOutSamples (modbase.h:114): samples available after the last pvgpu_process */
+int pvgpu_available(const pvgpu_stream *s);
+/* modbase_offline::getOutData (modbase.h:97, phasevocoder.cc:110-124): copies min(n, available); returns the count */
+int pvgpu_retrieve(pvgpu_stream *s, float *const *out, int n);
+/* modbase::processBlock (modbase.h:43, phasevocoder.cc:126-183): in place; returns 0 and sets *ready=1 when the
+ * block was replaced, or returns 0 with *ready=0 (buffer untouched) when fewer than n samples were available --
+ * i.e. *ready is modbase::outputReady() (modbase.h:61) */
+int pvgpu_process_block(pvgpu_stream *s, float *const *buf, int n, int *ready);
+int pvgpu_stream_info(const pvgpu_stream *s, pvgpu_info *info);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batch: many independent streams with one configuration, each processed exactly as one fresh
+ * `audiomod-exe <mode> in.wav out.wav ...` process would (main/main.cc:149,471-509: blocks of
+ * max(480, sr/100); pitch modes are flushed with zero blocks and truncated to the input length,
+ * time_stretch is not flushed).  Rows are channel-planar: row = stream * channels + channel.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pvgpu_batch pvgpu_batch;
+
+int pvgpu_batch_create(const pvgpu_config *cfg, int n_streams, int64_t max_in_samples, pvgpu_batch **out);
+void pvgpu_batch_destroy(pvgpu_batch *b);
+/* Fix the per-stream input lengths (samples per channel) and get the per-stream output lengths.
+ * block = 0 uses the CLI block size.  Must be called before a run; may be called again. */
+int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_out);
+/* Inputs and outputs resident in device memory: d_in [rows][in_stride], d_out [rows][out_stride]
+ * (elements of `fmt`), out_stride >= max n_out.  cuda_stream is a cudaStream_t (NULL = the batch's own
+ * stream); the call only enqueues work and does not synchronise when a stream is given. */
+int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt,
+                           void *cuda_stream);
+/* Host buffers (pinned or pageable): one pointer per row; copies in, runs, copies out, synchronises.
+ * Stream groups are pipelined so H2D, kernels and D2H overlap. */
+int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt);
+/* counters of the last run: kernels launched, slices per stream, H2D/D2H bytes */
+int pvgpu_batch_stats(const pvgpu_batch *b, int64_t *kernel_launches, int64_t *slices, int64_t *h2d_bytes, int64_t *d2h_bytes);
+int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);
+/* tuning: frames per chunk and rows per group (0 = keep) */
+int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage hooks for the parity tests (tests/ compares each stage with the CPU oracle).  Device work,
+ * host pointers.  frames: [n_frames][fftsize] raw (un-windowed) frames.
+ * ------------------------------------------------------------------------------------------- */
+/* analyzeSlice + FFT::forwardPolar (phasevocoderprocess.cc:492-503, FFT.cc:2617-2631) */
+int pvgpu_test_forward_polar(int device, int fftsize, int n_frames, const float *frames, float *mag, float *phase);
+/* 1/N scale + FFT::inversePolar + ifftshift + window (phasevocoderprocess.cc:1024-1056) */
+int pvgpu_test_inverse_polar(int device, int fftsize, int n_frames, const float *mag, const float *phase, float *frames);
+/* device atan2f restatement (FFT.cc:2629 -> glibc atan2f) */
+int pvgpu_test_atan2f(int device, int64_t n, const float *y, const float *x, float *out);
+/* princarg (src/common/system/sys.h:84-91) */
+int pvgpu_test_princarg(int device, int64_t n, const double *a, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVGPU_H_ */
