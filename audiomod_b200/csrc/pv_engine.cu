@@ -98,6 +98,37 @@ struct Pipeline {
     long recs_base = 0, recs_count = 0;
     int64_t norm_base = 0;
     int64_t launches = 0;
+    // optional per-kernel timing with CUDA events on the launching stream
+    bool profile = false;
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    size_t spans_used = 0;
+    double kind_ms[8] = {0};
+    int64_t kind_n[8] = {0};
+
+    ~Pipeline() { for (auto &sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); } }
+
+    Span *span_begin(int kind, cudaStream_t st) {
+        if (!profile) return nullptr;
+        if (spans_used == spans.size()) {
+            Span sp{kind, nullptr, nullptr};
+            if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return nullptr;
+            spans.push_back(sp);
+        }
+        Span *sp = &spans[spans_used++];
+        sp->kind = kind;
+        cudaEventRecord(sp->a, st);
+        return sp;
+    }
+    static void span_end(Span *sp, cudaStream_t st) { if (sp) cudaEventRecord(sp->b, st); }
+    // after the stream has been synchronised: fold the recorded spans into kind_ms / kind_n
+    void collect_spans() {
+        for (size_t i = 0; i < spans_used; ++i) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, spans[i].a, spans[i].b) == cudaSuccess) { kind_ms[spans[i].kind] += ms; kind_n[spans[i].kind] += 1; }
+        }
+        spans_used = 0;
+    }
 
     int init(const pvgpu_config &cfg) {
         int ndev = 0;
@@ -177,13 +208,20 @@ struct Pipeline {
     // Frames [k0, k0+nf) of the rows in g; the schedule for them must be on the device.
     void run_frames(const DevRows &g, long k0, int nf, cudaStream_t st) {
         const SliceRec *recs = b_recs.as<SliceRec>();
-        launch_analyse(p, g, k0, nf, st); ++launches;
-        if (d.robotic) { launch_fixed_phase(p, g, nullptr, k0, nf, st); ++launches; }
-        else if (d.whisper) { launch_fixed_phase(p, g, b_whisper.as<float>(), k0, nf, st); ++launches; }
-        else if (!d.vocoder && !d.constant_mode) { launch_phase_core(p, g, d.cfg.coremode, recs, recs_base, k0, nf, st); ++launches; }
-        launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st); ++launches;
-        launch_overlap_add(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, st); ++launches;
-        if (p.rs_active) { launch_resample(p, g, recs, recs_base, k0, nf, st); ++launches; }
+        Span *sp;
+        sp = span_begin(0, st); launch_analyse(p, g, k0, nf, st); span_end(sp, st); ++launches;
+        if (d.robotic || d.whisper) {
+            sp = span_begin(5, st);
+            launch_fixed_phase(p, g, d.whisper ? b_whisper.as<float>() : nullptr, k0, nf, st);
+            span_end(sp, st); ++launches;
+        } else if (!d.vocoder && !d.constant_mode) {
+            sp = span_begin(1, st); launch_phase_core(p, g, d.cfg.coremode, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches;
+        }
+        sp = span_begin(2, st);
+        launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st);
+        span_end(sp, st); ++launches;
+        sp = span_begin(3, st); launch_overlap_add(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, st); span_end(sp, st); ++launches;
+        if (p.rs_active) { sp = span_begin(4, st); launch_resample(p, g, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches; }
     }
 };
 
@@ -460,6 +498,23 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
         b->d2h += sizeof(float) * n;
     }
     CU(cudaStreamSynchronize(b->stream));
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_profile(pvgpu_batch *b, int enable) {
+    if (!b) return fail(PVGPU_EINVAL, "null batch");
+    b->pl.profile = enable != 0;
+    b->pl.spans_used = 0;
+    for (int i = 0; i < 8; ++i) { b->pl.kind_ms[i] = 0; b->pl.kind_n[i] = 0; }
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_kernel_times(pvgpu_batch *b, double *ms, int64_t *count) {
+    if (!b || !ms || !count) return fail(PVGPU_EINVAL, "null argument");
+    CU(cudaSetDevice(b->pl.device));
+    CU(cudaDeviceSynchronize());
+    b->pl.collect_spans();
+    for (int i = 0; i < 8; ++i) { ms[i] = b->pl.kind_ms[i]; count[i] = b->pl.kind_n[i]; }
     return PVGPU_OK;
 }
 

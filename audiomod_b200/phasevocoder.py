@@ -173,6 +173,18 @@ class PhaseVocoderBatch:
         self.run_host_rows(in_rows, out_rows)
         return outs
 
+    KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "overlap_add", "resample", "fixed_phase")
+
+    def profile(self, enable=True):
+        check(_lib.lib().pvgpu_batch_profile(self._h, int(bool(enable))))
+
+    def kernel_times(self) -> dict:
+        """{kernel kind: (total ms, launches)} since profile(True); synchronises the device."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        check(_lib.lib().pvgpu_batch_kernel_times(self._h, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNEL_KINDS)}
+
     def stats(self) -> dict:
         v = [C.c_int64() for _ in range(4)]
         check(_lib.lib().pvgpu_batch_stats(self._h, *[C.byref(x) for x in v]))

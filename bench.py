@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the batched phase-vocoder hot path (BASELINE.json metric: audio-seconds per wall-second,
+2048-point pitch shift, batched streams).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--secs T]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference      # the reference's own CPU path on the host cores
+
+Workload (config 4 of BASELINE.json): S = 4096 synthetic mono 44.1 kHz streams of 10 s PER GPU, +7 semitones,
+coremode 1 (phase locked), FFT 2048.  A step is one pass of the whole path over that batch.  `value` is measured with
+the inputs resident in HBM (7.2 GB of float32 PCM per GPU, far larger than L2); `e2e` goes through the host-buffer
+entry point (pinned host memory -> H2D -> kernels -> D2H) every step.  Streams are independent, so multi-GPU is one
+process per GPU with its own batch and no collective on the data path (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, SEMITONES, FFT, COREMODE, MODE = 44100, 7.0, 2048, 1, 0
+METRIC = "audio-sec/sec, 2048-pt PV pitch-shift, batched streams"
+UNIT = "audio-s/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--secs", type=float, default=10.0)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-chunk", type=int, default=0)
+    ap.add_argument("--rows-per-group", type=int, default=0)
+    ap.add_argument("--cpu-streams-per-core", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"{args.streams} synthetic mono {SR / 1000:g} kHz {args.secs:g} s streams per GPU, +{SEMITONES:g} semitones, "
+                        f"coremode {COREMODE}, FFT {FFT} (BASELINE.json configs[3])",
+            "streams_per_gpu": args.streams, "stream_seconds": args.secs, "sample_rate": SR, "semitones": SEMITONES, "fftsize": FFT,
+            "coremode": COREMODE, "channels": 1, "n_gpus": n_gpus, "sharding": "streams split across GPUs, no collective",
+            "l2": "inputs (7.2 GB/GPU at the default size) exceed the 126 MB L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU side: the unmodified reference (oracle/_ref/pvref_drv, one OS process per stream because the reference keeps
+# process-global state) or, if it was not built, the C restatement.  Only used for cpu_baseline / --impl reference.
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_run(n_streams: int, secs: float, cores: int):
+    """Process n_streams synthetic streams on `cores` host cores; returns (audio-s/s, kind, seconds)."""
+    from audiomod_b200.synth import synth
+    from oracle import pv_oracle as O
+    xs = [synth(4000 + i, SR, secs, 1) for i in range(n_streams)]
+    if O.have_ref():
+        kind = "reference"
+        with tempfile.TemporaryDirectory(prefix="pvbench_") as d:
+            for i, x in enumerate(xs):
+                x.tofile(os.path.join(d, f"i{i}.f32"))
+            cmds = [[O.REF_DRV, str(SR), "1", "1.0", repr(SEMITONES), str(MODE), str(COREMODE), str(FFT),
+                     os.path.join(d, f"i{i}.f32"), os.path.join(d, f"o{i}.f32")] for i in range(n_streams)]
+            t0 = time.perf_counter()
+            running, nxt = [], 0
+            while nxt < len(cmds) or running:
+                while nxt < len(cmds) and len(running) < cores:
+                    running.append(subprocess.Popen(cmds[nxt]))
+                    nxt += 1
+                p = running.pop(0)
+                if p.wait() != 0:
+                    raise RuntimeError("reference driver failed")
+            dt = time.perf_counter() - t0
+    else:
+        kind = "port"
+        import multiprocessing as mp
+        O.lib()
+        t0 = time.perf_counter()
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_port_one, xs)
+        dt = time.perf_counter() - t0
+    return n_streams * secs / dt, kind, dt
+
+
+def _port_one(x):
+    from oracle import pv_oracle as O
+    return O.run_offline(x, SR, semitones=SEMITONES, mode=MODE, coremode=COREMODE, fftsize=FFT).shape[1]
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = max(cores, cores * args.cpu_streams_per_core)
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(cores, min(args.secs, 2.0), cores)
+    vals, times, kind = [], [], "port"
+    for _ in range(args.steps):
+        v, kind, dt = cpu_run(n, args.secs, cores)
+        vals.append(v)
+        times.append(dt)
+    value = float(np.mean(vals))
+    sample = f"{n} of the workload's streams ({args.secs:g} s each) per step, one OS process per stream on {cores} cores"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def make_inputs(torch, dev, streams, n, seed):
+    """Seeded synthetic PCM generated on the GPU (same recipe family as audiomod_b200/synth.py): 8 harmonics with
+    vibrato and tremolo plus noise, quantised to int16 and presented as int16/32768 like the reference WAV reader."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    out = torch.empty((streams, n), dtype=torch.float32, device=dev)
+    t = torch.arange(n, dtype=torch.float64, device=dev) / SR
+    step = 64
+    for s0 in range(0, streams, step):
+        m = min(step, streams - s0)
+        u = torch.rand((m, 1), generator=g, device=dev, dtype=torch.float64) * 12 - 6
+        f0 = 110.0 * 2.0 ** (u / 12.0)
+        vph = torch.rand((m, 1), generator=g, device=dev, dtype=torch.float64) * 2 * np.pi
+        tph = torch.rand((m, 1), generator=g, device=dev, dtype=torch.float64) * 2 * np.pi
+        cyc = f0 * (t[None, :] - 0.01 / (2 * np.pi * 0.7) * torch.cos(2 * np.pi * 0.7 * t[None, :] + vph))
+        cyc = (cyc - torch.floor(cyc)).to(torch.float32) * (2 * np.pi)
+        x = torch.zeros((m, n), dtype=torch.float32, device=dev)
+        for k in range(8):
+            ph0 = torch.rand((m, 1), generator=g, device=dev, dtype=torch.float32) * (2 * np.pi)
+            x += (0.25 / (k + 1)) * torch.sin((k + 1) * cyc + ph0)
+        trem = (0.8 + 0.2 * torch.sin(2 * np.pi * 1.3 * t[None, :] + tph)).to(torch.float32)
+        x = x * trem + 0.01 * torch.randn((m, n), generator=g, device=dev, dtype=torch.float32)
+        q = torch.round(torch.clamp(x, -1.0, 1.0) * 32767.0)
+        out[s0:s0 + m] = (q.to(torch.float64) * (1.0 / 32768.0)).to(torch.float32)
+        del cyc, x, trem, q
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import audiomod_b200 as A
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the phase vocoder has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S, n = args.streams, int(round(SR * args.secs))
+    stride = (n + 3) & ~3
+    d_in = torch.zeros((S, stride), dtype=torch.float32, device=dev)
+    d_in[:, :n] = make_inputs(torch, dev, S, n, 1234 + rank)
+    batch = A.PhaseVocoderBatch(S, n, SR, 1, 1.0, SEMITONES, MODE, COREMODE, FFT, device=local)
+    if args.frames_per_chunk or args.rows_per_group:
+        batch.tune(args.frames_per_chunk, args.rows_per_group)
+    n_out = batch.plan(n)
+    out_stride = (int(n_out.max()) + 3) & ~3
+    d_out = torch.zeros((S, out_stride), dtype=torch.float32, device=dev)
+    info = batch.info()
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        batch.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), out_stride, stream.cuda_stream)
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    batch.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ktimes = batch.kernel_times()
+    batch.profile(False)
+    stats = batch.stats()
+    clocks = sampler.summary()
+    ms_step = ms_total / args.steps
+    audio_sec_per_step = world * S * args.secs
+    value = audio_sec_per_step / (ms_step / 1e3)
+    checksum = float(d_out[:, :int(n_out.min())].double().abs().mean().item())
+
+    # ---- roofline of the dominant kernel (staged-traffic model, DESIGN.md "Algorithmic bytes") ----
+    N, hop, H, half = info["fftsize"], info["hop"], info["bins"], info["fftsize"] // 2
+    slices = stats["slices"]
+    shift = hop * info["hs_ratio"]
+    per_frame = {"analyse": 4 * (hop + 2 * H), "phase_core": 4 * (2 * H + half), "synthesise": 4 * (2 * H + N),
+                 "overlap_add": 4 * (N + shift), "resample": 4 * (shift + shift / info["pitch_scale"])}
+    dom = max((k for k in per_frame if ktimes[k][1] > 0), key=lambda k: ktimes[k][0])
+    dom_ms, dom_launches = ktimes[dom]
+    bytes_total = per_frame[dom] * slices * S * args.steps
+    achieved = bytes_total / (dom_ms / 1e3) / 1e9
+    peak, peak_src = 6650.0, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    kernel_ms_sum = sum(v[0] for v in ktimes.values())
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_total / max(dom_launches, 1),
+                "avg_launch_ms": dom_ms / max(dom_launches, 1),
+                "kernel_share_of_step": dom_ms / max(kernel_ms_sum, 1e-9),
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
+                "compulsory_io_frac": (8.0 * n * S) / (ms_step / 1e3) / 1e9 / peak}
+
+    # ---- end to end through the host-buffer entry point ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.empty((S, stride), dtype=torch.float32, pin_memory=True)
+        h_in.copy_(d_in)
+        h_out = torch.empty((S, out_stride), dtype=torch.float32, pin_memory=True)
+        in_rows = [h_in.data_ptr() + 4 * stride * r for r in range(S)]
+        out_rows = [h_out.data_ptr() + 4 * out_stride * r for r in range(S)]
+        batch.run_host_rows(in_rows, out_rows)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            batch.run_host_rows(in_rows, out_rows)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0) / args.steps
+        st = batch.stats()
+        e2e = {"value": audio_sec_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] * world,
+               "d2h_bytes_per_step": st["d2h_bytes"] * world, "ms_per_step": dt * 1e3, "format": "f32 in, f32 out, pinned host memory",
+               "result_checksum": float(h_out[:, :int(n_out.min())].double().abs().mean().item())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        ncpu = max(cores, cores * args.cpu_streams_per_core)
+        v, kind, dt = cpu_run(ncpu, args.secs, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{ncpu} streams of the same workload ({args.secs:g} s each), one OS process per stream, {dt:.1f} s wall"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": stats["kernel_launches"] * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+                "result_checksum": checksum}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

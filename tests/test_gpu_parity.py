@@ -1,0 +1,324 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI (libpvgpu.so via ctypes); the CPU
+oracle and the golden vectors of the unmodified reference are only the checkers.
+
+Bars (BASELINE.json north_star): frame/hop indexing and sample counts exact; audio max-abs error <= 1e-4 of full scale
+and >= 90 dB SNR per channel.  Integer/bit work (the analysis FFT, magnitude, atan2f, princarg, robotic mode) is held
+to bit-exactness.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES, ctor_args, make_input
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 1e-4
+MIN_SNR_DB = 90.0
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pv_golden.npz")
+_fp = C.POINTER(C.c_float)
+
+
+def _p(a):
+    return a.ctypes.data_as(_fp)
+
+
+def assert_parity(y, ref, what=""):
+    assert y.shape == ref.shape, f"{what}: sample count {y.shape} != reference {ref.shape}"
+    for c in range(ref.shape[0]):
+        err = y[c].astype(np.float64) - ref[c].astype(np.float64)
+        mx = float(np.max(np.abs(err))) if err.size else 0.0
+        e = float(np.sum(err ** 2))
+        pw = float(np.sum(ref[c].astype(np.float64) ** 2))
+        snr = 10 * np.log10(pw / e) if e > 0 and pw > 0 else float("inf")
+        assert mx <= MAX_ABS, f"{what} ch{c}: max-abs {mx:.3e}"
+        assert snr >= MIN_SNR_DB, f"{what} ch{c}: SNR {snr:.1f} dB"
+
+
+@pytest.fixture(scope="module")
+def A(pvlib):
+    import audiomod_b200
+    if pvlib.pvgpu_device_count() < 1:
+        pytest.fail("no CUDA device: GPU tests must run on the B200 box")
+    return audiomod_b200
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stage-level, bit-exact
+# ---------------------------------------------------------------------------------------------------------------
+def test_device_atan2f_bit_exact(A, pvlib, oracle):
+    rng = np.random.default_rng(7)
+    n = 1 << 21
+    y = rng.standard_normal(n).astype(np.float32) * np.float32(10.0) ** rng.integers(-6, 3, n).astype(np.float32)
+    x = rng.standard_normal(n).astype(np.float32) * np.float32(10.0) ** rng.integers(-6, 3, n).astype(np.float32)
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3.4e38, 0.4375, 0.6875, 1.1875, 2.4375], np.float32)
+    yy, xx = np.meshgrid(sp, sp)
+    y = np.concatenate([y, yy.ravel()]).astype(np.float32)
+    x = np.concatenate([x, xx.ravel()]).astype(np.float32)
+    out = np.zeros_like(y)
+    assert pvlib.pvgpu_test_atan2f(0, y.size, _p(y), _p(x), _p(out)) == 0
+    ref = oracle.host_atan2f(y, x)
+    same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
+    assert same.all(), f"{(~same).sum()} mismatches"
+
+
+def test_device_princarg_bit_exact(A, pvlib, oracle):
+    rng = np.random.default_rng(8)
+    a = np.concatenate([rng.uniform(-40, 40, 200000), np.pi * np.arange(-9, 10), np.float32(np.pi) * np.arange(-9, 10),
+                        rng.standard_normal(1000) * 1e-6, [0.0, -0.0, 700.25, -1234.5]]).astype(np.float64)
+    out = np.zeros_like(a)
+    dp = C.POINTER(C.c_double)
+    assert pvlib.pvgpu_test_princarg(0, a.size, a.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+    ref = np.array([oracle.lib().pvo_princarg(float(v)) for v in a])
+    assert np.array_equal(out.view(np.uint64), ref.view(np.uint64))
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
+def test_forward_polar_bit_exact(A, pvlib, oracle, n):
+    """Hann + fftshift + KissFFT-order real FFT + sqrtf/atan2f: every bin bit-identical."""
+    from audiomod_b200.synth import synth
+    rng = np.random.default_rng(n)
+    nf = 12
+    frames = np.stack([synth(n + i, 44100, n / 44100.0 + 0.01, 1)[0, :n] for i in range(nf - 3)]
+                      + [rng.standard_normal(n).astype(np.float32) * 0.3, np.zeros(n, np.float32),
+                         np.full(n, 0.25, np.float32)]).astype(np.float32)
+    frames = np.ascontiguousarray(frames)
+    h = n // 2 + 1
+    mag, ph = np.zeros((nf, h), np.float32), np.zeros((nf, h), np.float32)
+    assert pvlib.pvgpu_test_forward_polar(0, n, nf, _p(frames), _p(mag), _p(ph)) == 0
+    for i in range(nf):
+        rm, rp, _ = oracle.forward_polar(frames[i])
+        assert np.array_equal(mag[i].view(np.uint32), rm.view(np.uint32)), f"magnitude differs, frame {i}"
+        assert np.array_equal(ph[i].view(np.uint32), rp.view(np.uint32)), f"phase differs, frame {i}"
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096, 8192])
+def test_inverse_polar_close(A, pvlib, oracle, n):
+    rng = np.random.default_rng(n + 1)
+    nf, h = 6, n // 2 + 1
+    mag = (np.abs(rng.standard_normal((nf, h))) * 50).astype(np.float32)
+    ph = rng.uniform(-np.pi, np.pi, (nf, h)).astype(np.float32)
+    out = np.zeros((nf, n), np.float32)
+    assert pvlib.pvgpu_test_inverse_polar(0, n, nf, _p(mag), _p(ph), _p(out)) == 0
+    for i in range(nf):
+        ref = oracle.inverse_polar(mag[i] * np.float32(1.0 / n), ph[i], n)  # the device stage includes the 1/N scale
+        assert np.max(np.abs(out[i] - ref)) <= 2e-6 * max(1.0, float(np.max(np.abs(ref))))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole path: batch entry point
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_batch_matches_reference_golden(A, gold, case):
+    """Golden vectors of the unmodified reference; three ragged copies exercise per-stream lengths."""
+    name, kw, sr, ch, secs, seed = case
+    x = make_input(name, sr, ch, secs, seed)
+    tr, st, mode, core, fft = ctor_args(kw)
+    b = A.PhaseVocoderBatch(1, x.shape[1], sr, ch, tr, st, mode, core, fft)
+    (y,) = b.run([x])
+    assert b.stats()["kernel_launches"] > 0
+    b.close()
+    assert_parity(y, gold[name + "__out"], name)
+    if mode == A.ROBOTIC:
+        assert np.array_equal(y.view(np.uint32), gold[name + "__out"].view(np.uint32))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_batch_ragged_matches_oracle(A, oracle, case):
+    name, kw, sr, ch, secs, seed = case
+    tr, st, mode, core, fft = ctor_args(kw)
+    xs = [make_input(name, sr, ch, secs * f, seed + 11 * i) for i, f in enumerate((1.3, 0.31, 0.9, 0.05))]
+    ref = [oracle.run_offline(x, sr, **kw) for x in xs]
+    b = A.PhaseVocoderBatch(len(xs), max(x.shape[1] for x in xs), sr, ch, tr, st, mode, core, fft)
+    b.tune(frames_per_chunk=7)   # odd chunking: state must carry across chunk boundaries
+    ys = b.run(xs)
+    b.close()
+    for i, (y, r) in enumerate(zip(ys, ref)):
+        assert_parity(y, r, f"{name}[{i}]")
+
+
+def test_empty_and_tiny_streams(A, oracle):
+    sr = 44100
+    xs = [np.zeros((1, 0), np.float32), make_input("x", sr, 1, 0.001, 1), make_input("x", sr, 1, 0.05, 2), make_input("x", sr, 1, 0.3, 3)]
+    ref = [oracle.run_offline(x, sr, semitones=7.0) for x in xs]
+    b = A.PhaseVocoderBatch(len(xs), max(x.shape[1] for x in xs), sr, 1, 1.0, 7.0)
+    ys = b.run(xs)
+    b.close()
+    for i, (y, r) in enumerate(zip(ys, ref)):
+        assert_parity(y, r, f"tiny[{i}]")
+
+
+def test_batch_invariance_bitwise(A):
+    """A stream's result does not depend on what else is in the batch nor on chunk / group tuning."""
+    sr = 44100
+    xs = [make_input("x", sr, 2, 0.4, 40 + i) for i in range(6)]
+    outs = []
+    for fpc, rpg, order in ((64, 0, range(6)), (5, 4, reversed(range(6))), (1, 2, range(6))):
+        order = list(order)
+        b = A.PhaseVocoderBatch(6, xs[0].shape[1], sr, 2, 1.0, 4.0)
+        b.tune(fpc, rpg)
+        ys = b.run([xs[i] for i in order])
+        b.close()
+        outs.append({i: ys[j] for j, i in enumerate(order)})
+    for i in range(6):
+        assert np.array_equal(outs[0][i], outs[1][i]) and np.array_equal(outs[0][i], outs[2][i])
+
+
+def test_stereo_identical_channels_quirk(A, oracle):
+    """The reference shares the peak lists between the channels of a stream, so with L == R channel 0 equals the mono
+    result bit for bit while channel 1 does not.  The GPU path must reproduce exactly that."""
+    sr = 44100
+    m = make_input("x", sr, 1, 0.5, 77)
+    st = np.concatenate([m, m], axis=0)
+    bm = A.PhaseVocoderBatch(1, m.shape[1], sr, 1, 1.0, 4.0)
+    (ym,) = bm.run([m])
+    bm.close()
+    bs = A.PhaseVocoderBatch(1, m.shape[1], sr, 2, 1.0, 4.0)
+    (ys,) = bs.run([st])
+    bs.close()
+    assert np.array_equal(ys[0], ym[0])
+    rs = oracle.run_offline(st, sr, semitones=4.0)
+    assert_parity(ys, rs, "L==R")
+    assert not np.array_equal(rs[0], rs[1])
+
+
+def test_device_resident_entry_point(A, oracle):
+    """pvgpu_batch_run_device with caller-owned device buffers (torch tensors) on torch's current stream."""
+    torch = pytest.importorskip("torch")
+    sr, S = 44100, 5
+    xs = [make_input("x", sr, 1, 0.3, 300 + i) for i in range(S)]
+    n = xs[0].shape[1]
+    b = A.PhaseVocoderBatch(S, n, sr, 1, 1.0, 7.0)
+    n_out = b.plan(n)
+    stride, ostride = (n + 3) & ~3, (int(n_out.max()) + 3) & ~3
+    d_in = torch.zeros((S, stride), dtype=torch.float32, device="cuda")
+    d_in[:, :n] = torch.from_numpy(np.concatenate(xs, axis=0)).cuda()
+    d_out = torch.full((S, ostride), 7.0, dtype=torch.float32, device="cuda")
+    b.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), ostride, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    y = d_out.cpu().numpy()
+    b.close()
+    for i in range(S):
+        assert_parity(y[i:i + 1, :int(n_out[i])], oracle.run_offline(xs[i], sr, semitones=7.0), f"dev[{i}]")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# streaming instance: the modbase / modbase_offline calls
+# ---------------------------------------------------------------------------------------------------------------
+def _cli_protocol(pv, x, sr, mode, block=0):
+    B = block or max(480, sr // 100)
+    n, ch = x.shape[1], x.shape[0]
+    chunks, produced = [], 0
+    for i in range(0, n, B):
+        pv.processInData(x[:, i:i + B])
+        y = pv.getOutData(pv.getOutSamples())
+        chunks.append(y.copy())
+        produced += y.shape[1]
+    if mode != 5:
+        z = np.zeros((ch, B), np.float32)
+        while produced < n:
+            pv.processInData(z)
+            y = pv.getOutData(pv.getOutSamples())
+            if n - produced <= y.shape[1]:
+                y = y[:, :n - produced]
+            chunks.append(y.copy())
+            produced += y.shape[1]
+    return np.concatenate(chunks, axis=1)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[0] in ("cfg1_shift_p4_stereo", "cfg2_stretch_1p5_4096", "cfg3_gender_m4",
+                                                               "cfg5_whisper_1024", "cfg5_chord_4096", "core0_shift_p3_stereo",
+                                                               "constant_1024", "core2_octave_up")],
+                         ids=lambda c: c[0])
+def test_streaming_offline_api_matches_golden(A, gold, case):
+    name, kw, sr, ch, secs, seed = case
+    x = make_input(name, sr, ch, secs, seed)
+    tr, st, mode, core, fft = ctor_args(kw)
+    pv = A.phasevocoder(sr, ch, tr, st, mode, core, fft)
+    y = _cli_protocol(pv, x, sr, mode)
+    pv.close()
+    assert_parity(y, gold[name + "__out"], name)
+
+
+@pytest.mark.parametrize("name", ["cfg4_shift_p7_mono", "cfg5_robotic_512"])
+def test_streaming_process_block_matches_golden(A, gold, name):
+    """In-place processBlock / outputReady loop of the SDK (README usage, main.cc:562-571)."""
+    kw, sr, ch, secs, seed = next((c[1], c[2], c[3], c[4], c[5]) for c in CASES if c[0] == name)
+    x = make_input(name, sr, ch, secs, seed)
+    tr, st, mode, core, fft = ctor_args(kw)
+    pv = A.phasevocoder(sr, ch, tr, st, mode, core, fft)
+    B = max(480, sr // 100)
+    kept, dropped = [], 0
+    for i in range(0, x.shape[1], B):
+        blk = np.ascontiguousarray(x[:, i:i + B])
+        before = blk.copy()
+        pv.processBlock(blk)
+        if pv.outputReady():
+            kept.append(blk)
+        else:
+            dropped += 1
+            assert np.array_equal(blk, before), "buffer must be untouched when output is not ready"
+    pv.close()
+    y = np.concatenate(kept, axis=1)
+    assert dropped > 0
+    assert_parity(y, gold[name + "__rt"], name + " rt")
+
+
+def test_streaming_odd_block_sizes(A, oracle):
+    """Arbitrary call sizes (0, 1, primes, several windows at once) give the oracle's per-call counts and samples."""
+    sr = 44100
+    x = make_input("x", sr, 2, 0.7, 91)
+    pv = A.phasevocoder(sr, 2, 1.0, -3.0, 0, 1, 1024)
+    st = oracle.OracleStream(sr, 2, 1.0, -3.0, 0, 1, 1024)
+    sizes = [0, 1, 7, 1023, 1, 4099, 0, 480, 2500, 311]
+    pos, k = 0, 0
+    while pos < x.shape[1]:
+        n = min(sizes[k % len(sizes)], x.shape[1] - pos)
+        k += 1
+        blk = np.ascontiguousarray(x[:, pos:pos + n])
+        pv.processInData(blk)
+        st.processInData(blk)
+        assert pv.getOutSamples() == st.getOutSamples()
+        take = pv.getOutSamples() if k % 3 else pv.getOutSamples() // 2   # sometimes leave samples in the ring
+        a, b = pv.getOutData(take), st.getOutData(take)
+        assert_parity(a, b, f"call {k}")
+        pos += n
+    pv.close()
+    st.close()
+
+
+def test_unknown_mode_does_nothing(A):
+    pv = A.phasevocoder(44100, 1, 1.0, 0.0, 42, 1, 2048)
+    pv.processInData(np.zeros((1, 4800), np.float32))
+    assert pv.getOutSamples() == 0
+    pv.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-size workload: size-independent properties (the oracle would take minutes here)
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_length_streams_properties(A, oracle):
+    """BASELINE config 4 shape at reduced stream count: 10 s streams, +7 semitones, FFT 2048.  Output length equals the
+    input length for every stream, duplicate streams are bit-identical, and three streams are checked against the
+    oracle end to end."""
+    sr, secs, S = 44100, 10.0, 24
+    base = [make_input("x", sr, 1, secs, 4000 + i) for i in range(3)]
+    xs = [base[i % 3] for i in range(S)]
+    b = A.PhaseVocoderBatch(S, xs[0].shape[1], sr, 1, 1.0, 7.0)
+    ys = b.run(xs)
+    st = b.stats()
+    b.close()
+    assert st["slices"] == A.plan_counts(xs[0].shape[1], sr, 1, 1.0, 7.0)["n_slices"]
+    for i in range(S):
+        assert ys[i].shape == (1, 441000)
+        assert np.array_equal(ys[i], ys[i % 3])
+        assert np.isfinite(ys[i]).all()
+    for i in range(3):
+        assert_parity(ys[i], oracle.run_offline(base[i], sr, semitones=7.0), f"full[{i}]")

@@ -1,0 +1,121 @@
+"""Host side of the product on CPU: the data-independent slice schedule against the oracle's counts, the derived
+sizes, the C-ABI surface, and the loud failure without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CONFIGS = [
+    (dict(semitones=4, mode=0, fftsize=2048), 44100, 2),
+    (dict(timeratio=1.5, mode=5, fftsize=4096), 48000, 2),
+    (dict(semitones=7, mode=0, fftsize=2048), 44100, 1),
+    (dict(semitones=-4, mode=2, fftsize=2048), 44100, 1),
+    (dict(semitones=0, mode=1, fftsize=2048), 44100, 1),
+    (dict(semitones=12, mode=0, coremode=2, fftsize=2048), 44100, 1),
+    (dict(semitones=-12, mode=0, fftsize=1024), 22050, 1),
+    (dict(timeratio=0.7, mode=5, fftsize=1024), 44100, 1),
+    (dict(timeratio=2.0, mode=5, fftsize=512), 44100, 1),
+    (dict(mode=6, fftsize=8192), 44100, 2),
+    (dict(mode=3, fftsize=512), 44100, 2),
+    (dict(mode=-1, semitones=3, fftsize=1024), 44100, 1),
+    (dict(semitones=5, timeratio=1.3, mode=0, fftsize=2048), 44100, 1),
+    (dict(semitones=7, mode=0, fftsize=1000), 44100, 1),   # non power of two -> rounded up like the reference
+]
+
+
+@pytest.mark.parametrize("kw,sr,ch", CONFIGS)
+def test_plan_counts_match_oracle(pvlib, oracle, kw, sr, ch):
+    import audiomod_b200 as A
+    for n in (0, 1, 479, 480, 5000, 44100, 100003):
+        x = np.zeros((ch, n), np.float32)
+        y, slices = oracle.run_offline(x, sr, return_slices=True, **kw)
+        c = A.plan_counts(n, sr, ch, kw.get("timeratio", 1.0), kw.get("semitones", 0.0), kw.get("mode", 0), kw.get("coremode", 1),
+                          kw.get("fftsize", 2048))
+        assert (c["n_out"], c["n_slices"], c["n_dropped"]) == (y.shape[1], slices, 0), (kw, n)
+
+
+def test_survey_probe_counts(pvlib):
+    """Sample counts the survey measured on the unmodified reference."""
+    import audiomod_b200 as A
+    assert A.plan_counts(441000, 44100, 1, 1.0, 7.0)["n_out"] == 441000
+    c = A.plan_counts(472320, 48000, 2, 1.5, 0.0, A.NORMAL_STRETCH, 1, 4096)
+    assert c["n_out"] > 0 and c["n_dropped"] == 0
+
+
+def test_describe_matches_oracle_sizes(pvlib, oracle):
+    import audiomod_b200 as A
+    for kw, sr, ch in CONFIGS:
+        d = A.describe(sr, ch, kw.get("timeratio", 1.0), kw.get("semitones", 0.0), kw.get("mode", 0), kw.get("coremode", 1),
+                       kw.get("fftsize", 2048))
+        st = oracle.OracleStream(sr, ch, kw.get("timeratio", 1.0), kw.get("semitones", 0.0), kw.get("mode", 0), kw.get("coremode", 1),
+                                 kw.get("fftsize", 2048))
+        assert d["hop"] == st.hop and d["fftsize"] == oracle.lib().pvo_fftsize(st.h)
+        assert d["pitch_scale"] == oracle.lib().pvo_pitch_scale(st.h)
+        st.close()
+    # values the survey read from the reference's own log lines
+    assert A.describe(44100, 2, 1.0, 4.0)["hop"] == 203
+    assert A.describe(48000, 2, 1.5, 0.0, A.NORMAL_STRETCH, 1, 4096)["hop"] == 341
+    assert A.describe(44100, 1, 1.0, 7.0)["hop"] == 170
+    assert A.describe(44100, 1, 1.0, 7.0)["resampler_filt_len"] == 96
+    assert A.describe(44100, 1, 1.0, 4.0)["resampler_filt_len"] == 80
+
+
+def test_resampler_table_matches_oracle(pvlib, oracle):
+    """Same fraction and filter length as the oracle's Speex restatement."""
+    import audiomod_b200 as A
+    for st in (4.0, 7.0, 12.0, -4.0, -12.0, 0.5):
+        d = A.describe(44100, 1, 1.0, st)
+        r = oracle.resampler_params(d["pitch_scale"])
+        assert (d["resampler_num"], d["resampler_den"], d["resampler_filt_len"]) == (r["num"], r["den"], r["filt_len"])
+
+
+def test_c_abi_exports_every_declared_symbol(pvlib):
+    hdr = open(os.path.join(ROOT, "include", "pvgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(pvgpu_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    so = C.CDLL(os.path.join(ROOT, "audiomod_b200", "libpvgpu.so"))
+    missing = [n for n in sorted(names) if not hasattr(so, n)]
+    assert not missing, missing
+    from audiomod_b200 import _lib
+    assert set(_lib.SYMBOLS) == names
+
+
+def test_invalid_arguments_return_codes(pvlib):
+    import audiomod_b200 as A
+    from audiomod_b200 import _lib
+    with pytest.raises(A.PvgpuError) as e:
+        A.describe(44100, 0, 1.0, 0.0)
+    assert e.value.code == _lib.EINVAL
+    with pytest.raises(A.PvgpuError):
+        A.describe(44100, 1, 1.0, 0.0, fftsize=1 << 20)
+    assert pvlib.pvgpu_version() >= 100
+
+
+def test_no_gpu_fails_loudly(pvlib):
+    """There is no CPU fallback: without a device every create call reports PVGPU_ECUDA."""
+    import audiomod_b200 as A
+    from audiomod_b200 import _lib
+    if pvlib.pvgpu_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(A.PvgpuError) as e:
+        A.phasevocoder(44100, 1, 1.0, 7.0)
+    assert e.value.code == _lib.ECUDA
+    with pytest.raises(A.PvgpuError) as e:
+        A.PhaseVocoderBatch(4, 1000, 44100, 1, 1.0, 7.0)
+    assert e.value.code == _lib.ECUDA
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/."""
+    for base, _, files in os.walk(os.path.join(ROOT, "audiomod_b200")):
+        if "build" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".hpp")) or f == "Makefile":
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "pv_oracle" not in txt and "libpv_oracle" not in txt and "oracle/" not in txt.replace("the CPU oracle", ""), os.path.join(base, f)

@@ -1,0 +1,64 @@
+"""The oracle (oracle/pv_oracle.c) is pinned bit-exactly against golden vectors taken from the unmodified reference
+(tests/golden/make_golden.py) and, where oracle/_ref has been built, against the reference itself run live."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES, make_input
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pv_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_reference_golden(oracle, gold, case):
+    name, kw, sr, ch, secs, seed = case
+    pcm = gold[name + "__in"]
+    x = (pcm.astype(np.float64) * (1.0 / 32768.0)).astype(np.float32)
+    assert np.array_equal(x, make_input(name, sr, ch, secs, seed)), "synthetic input generator drifted from the fixture"
+    y = oracle.run_offline(x, sr, **kw)
+    ref = gold[name + "__out"]
+    assert y.shape == ref.shape
+    assert np.array_equal(y.view(np.uint32), ref.view(np.uint32)), "oracle is not bit-exact with the reference"
+
+
+@pytest.mark.parametrize("name", ["cfg4_shift_p7_mono", "cfg5_robotic_512"])
+def test_oracle_realtime_protocol_golden(oracle, gold, name):
+    """processBlock / outputReady loop (main.cc:562-571): blocks are kept only when outputReady()."""
+    kw, sr, ch, secs, seed = next((c[1], c[2], c[3], c[4], c[5]) for c in CASES if c[0] == name)
+    x = make_input(name, sr, ch, secs, seed)
+    st = oracle.OracleStream(sr, ch, kw.get("timeratio", 1.0), kw.get("semitones", 0.0), kw.get("mode", 0), kw.get("coremode", 1),
+                             kw.get("fftsize", 2048))
+    B = max(480, sr // 100)
+    kept = []
+    for i in range(0, x.shape[1], B):
+        blk = np.ascontiguousarray(x[:, i:i + B])
+        if st.processBlock(blk):
+            kept.append(blk)
+    y = np.concatenate(kept, axis=1) if kept else np.zeros((ch, 0), np.float32)
+    ref = gold[name + "__rt"]
+    assert y.shape == ref.shape and np.array_equal(y.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("case", CASES[::4], ids=[c[0] for c in CASES[::4]])
+def test_oracle_matches_live_reference(oracle, case):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    name, kw, sr, ch, secs, seed = case
+    x = make_input(name, sr, ch, secs * 1.7, seed + 77)
+    a, b = oracle.run_offline(x, sr, **kw), oracle.run_ref(x, sr, **kw)
+    assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_block_size_independence(oracle):
+    """Output does not depend on the block size as long as the ring never overflows."""
+    from audiomod_b200.synth import synth
+    x = synth(9, 44100, 0.5, 1)
+    a = oracle.run_offline(x, 44100, semitones=7.0, block=480)
+    b = oracle.run_offline(x, 44100, semitones=7.0, block=4410)
+    assert np.array_equal(a, b)
