@@ -18,35 +18,10 @@
 // contracts into FMAs, in the reference's operation order.  The synthesis side (inverse FFT, OLA,
 // resampler) is held to the 1e-4 / 90 dB tolerance and may use FMA.
 #include "pv_kernels.cuh"
+#include "pv_fft.cuh"
 #include "pv_math.cuh"
 
 namespace pvgpu {
-
-// ------------------------------------------------------------------------------------------------
-// complex helpers in the reference's operation order (_kiss_fft_guts.h:87-89, kiss_fft.c:36-104)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cmul_rn(float2 a, float2 b) {
-    return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
-}
-__device__ __forceinline__ float2 cadd_rn(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-__device__ __forceinline__ float2 csub_rn(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
-
-template <bool kInverse>
-__device__ __forceinline__ void bfly4(float2 &f0, float2 &f1, float2 &f2, float2 &f3, float2 t1, float2 t2, float2 t3) {
-    const float2 s0 = cmul_rn(f1, t1), s1 = cmul_rn(f2, t2), s2 = cmul_rn(f3, t3);
-    const float2 s5 = csub_rn(f0, s1);
-    f0 = cadd_rn(f0, s1);
-    const float2 s3 = cadd_rn(s0, s2), s4 = csub_rn(s0, s2);
-    f2 = csub_rn(f0, s3);
-    f0 = cadd_rn(f0, s3);
-    if (kInverse) {
-        f1 = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
-        f3 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
-    } else {
-        f1 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
-        f3 = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
-    }
-}
 
 // All butterfly stages of the nc-point complex FFT, in place in shared memory (data already permuted).
 template <bool kInverse>
@@ -126,6 +101,80 @@ __global__ void k_analyse(const DevPlan p, const DevRows g, long k0) {
             }
             mag[nc - kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
             ph[nc - kk] = pv_atan2f(bi, br);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_analyse_t<N>: register-tiled version for N = 512..8192 (pv_fft.cuh).  T = N/32 threads own a frame; a CTA of
+// max(T, 256) threads handles 256/T consecutive frames of the chunk.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(const DevPlan p, const DevRows g, long k0, int nf, int total) {
+    constexpr int NC = N / 2;
+    using S = FftShape<NC>;
+    constexpr int T = S::kThreads;
+    constexpr int G = (T >= 256) ? 1 : 256 / T;
+    extern __shared__ float2 sbuf[];
+    const int group = threadIdx.x / T, t = threadIdx.x % T;
+    float2 *buf = sbuf + group * S::kPadded;
+    const int fid = blockIdx.x * G + group;
+    const bool active = fid < total;   // whole groups are active or not, so group barriers stay consistent
+    const int row = active ? fid / nf : 0, f = active ? fid % nf : 0;
+    if (active) {
+        const long k = k0 + f;
+        const float *__restrict__ x = g.in + (int64_t)row * g.in_stride;
+        const int64_t start = (int64_t)k * p.hop;
+        const int64_t nvalid = g.n_in[row];
+        const float2 *__restrict__ w2 = (const float2 *)p.window;
+        // gather + Hann + fftshift + KissFFT input permutation, one complex (two consecutive samples) at a time
+#pragma unroll 4
+        for (int cc = t; cc < NC; cc += T) {
+            const int64_t gi = start + 2 * cc;
+            const float x0 = gi < nvalid ? x[gi - g.in_base] : 0.f;
+            const float x1 = gi + 1 < nvalid ? x[gi + 1 - g.in_base] : 0.f;
+            const float2 w = __ldg(&w2[cc]);
+            const int c = (cc + NC / 2) & (NC - 1);   // fftshift moves sample i to (i + N/2) mod N, i.e. complex cc to cc + NC/2
+            buf[fft_pad(fft_slot_of_input<NC>(c))] = make_float2(__fmul_rn(x0, w.x), __fmul_rn(x1, w.y));
+        }
+    }
+    frame_sync<T>(group);
+    float2 v[16];
+    if (active) fft_frame<NC, false>(v, buf, t, group, p.tw_fwd);
+    else { if (NC > 256) { frame_sync<T>(group); } frame_sync<T>(group); }
+    frame_sync<T>(group);   // all reads of the last pass are done before the natural-order write-back
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) buf[fft_pad(fft_out_index<NC>(t, i))] = v[i];
+    }
+    frame_sync<T>(group);
+    if (!active) return;
+    // real-FFT post-pass (kiss_fftr.c:67-121) + polar (FFT.cc:2617-2631)
+    float *__restrict__ mag = g.mag + ((int64_t)row * g.F + f) * p.Hp;
+    float *__restrict__ ph = g.phase + ((int64_t)row * g.F + f) * p.Hp;
+    const float2 *__restrict__ stw = p.stw_fwd;
+    for (int kk = t; kk <= NC / 2; kk += T) {
+        if (kk == 0) {
+            const float2 z = buf[fft_pad(0)];
+            const float dc = __fadd_rn(z.x, z.y), ny = __fsub_rn(z.x, z.y);
+            mag[0] = __fsqrt_rn(__fadd_rn(__fmul_rn(dc, dc), 0.f));
+            ph[0] = pv_atan2f(0.f, dc);
+            mag[NC] = __fsqrt_rn(__fadd_rn(__fmul_rn(ny, ny), 0.f));
+            ph[NC] = pv_atan2f(0.f, ny);
+        } else {
+            const float2 fpk = buf[fft_pad(kk)];
+            const float2 fq = buf[fft_pad(NC - kk)];
+            const float2 fpnk = make_float2(fq.x, -fq.y);
+            const float2 f1k = cadd_rn(fpk, fpnk), f2k = csub_rn(fpk, fpnk);
+            const float2 tw = cmul_rn(f2k, __ldg(&stw[kk]));
+            const float ar = __fmul_rn(__fadd_rn(f1k.x, tw.x), 0.5f), ai = __fmul_rn(__fadd_rn(f1k.y, tw.y), 0.5f);
+            const float br = __fmul_rn(__fsub_rn(f1k.x, tw.x), 0.5f), bi = __fmul_rn(__fsub_rn(tw.y, f1k.y), 0.5f);
+            if (kk != NC - kk) {  // bin NC/2 is written twice by the reference; the second write wins
+                mag[kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
+                ph[kk] = pv_atan2f_fast(ai, ar);
+            }
+            mag[NC - kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+            ph[NC - kk] = pv_atan2f_fast(bi, br);
         }
     }
 }
@@ -398,6 +447,107 @@ __global__ void k_synthesise(const DevPlan p, const DevRows g, const float *__re
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_synthesise_t<N>: register-tiled version (pv_fft.cuh).  Each thread builds the two packed bins kk and NC-kk straight
+// from global memory (the frequency warp and the vocoder modulation are gathers from the unmodified spectrum), writes
+// the inverse pre-pass result at its permuted slot, runs the inverse FFT in registers and stores the windowed,
+// ifft-shifted frame with 8-byte stores.
+// ------------------------------------------------------------------------------------------------
+struct SynthBinLoader {
+    const DevPlan &p;
+    const float *__restrict__ gmag, *__restrict__ gph, *__restrict__ cmag, *__restrict__ cph;
+    __device__ __forceinline__ float2 operator()(int i) const {
+        const int hs = p.half;
+        float m, ph;
+        if (cmag != nullptr) {  // modifySliceVocoder (:755-776)
+            m = cmag[i];
+            ph = cph[i];
+            const int band_len = p.N / 1024;
+            if (i == 0 || i == hs) {
+                m = 0.f;
+            } else if (band_len > 0) {
+                const int bs = (i / band_len) * band_len;
+                float mean = 0.f;
+                for (int e = 0; e < band_len; ++e) mean = __fadd_rn(mean, gmag[bs + e]);
+                m = __fmul_rn(m, __fdiv_rn(mean, (float)(band_len * 2)));
+            }
+        } else if (p.freq_comp != 0.f) {  // freqCompSlice (:842-923) as a gather
+            if (p.freq_comp > 1.0f || i < hs) {
+                const int src = __float2int_rn(__fmul_rn((float)i, p.freq_comp));
+                if (src > hs) {
+                    m = 0.f; ph = 0.f;
+                } else {
+                    const float dw = (float)__ddiv_rn(__dmul_rn(p.two_pi_hop, (double)(i - src)), (double)p.N);
+                    m = gmag[src];
+                    ph = __fadd_rn(gph[src], dw);
+                }
+            } else {
+                m = gmag[i]; ph = gph[i];
+            }
+            m = __fmul_rn(m, p.fixed_gain);
+        } else {
+            m = gmag[i]; ph = gph[i];
+        }
+        m = __fmul_rn(m, p.inv_n);
+        float sn, cs;
+        sincosf(ph, &sn, &cs);
+        return make_float2(m * cs, m * sn);
+    }
+};
+
+template <int N>
+__global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(const DevPlan p, const DevRows g, const float *__restrict__ car_mag,
+                                                                                 const float *__restrict__ car_phase, long k0, int nf, int total) {
+    constexpr int NC = N / 2;
+    using S = FftShape<NC>;
+    constexpr int T = S::kThreads;
+    constexpr int G = (T >= 256) ? 1 : 256 / T;
+    extern __shared__ float2 sbuf[];
+    const int group = threadIdx.x / T, t = threadIdx.x % T;
+    float2 *buf = sbuf + group * S::kPadded;
+    const int fid = blockIdx.x * G + group;
+    const bool active = fid < total;
+    const int row = active ? fid / nf : 0, f = active ? fid % nf : 0;
+    const long k = k0 + f;
+    if (active) {
+        const int64_t so = ((int64_t)row * g.F + f) * p.Hp;
+        const int64_t co = (int64_t)(k - g.aux_base) * p.Hp;
+        const SynthBinLoader bin{p, g.mag + so, g.phase + so, car_mag ? car_mag + co : nullptr, car_mag ? car_phase + co : nullptr};
+        const float2 *__restrict__ stw = p.stw_inv;
+        for (int kk = t; kk <= NC / 2; kk += T) {  // inverse real-FFT pre-pass (kiss_fftr.c:123-159)
+            const float2 fk = bin(kk);
+            const float2 fq = bin(NC - kk);
+            if (kk == 0) {
+                buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk.x + fq.x, fk.x - fq.x);
+            } else {
+                const float2 fnkc = make_float2(fq.x, -fq.y);
+                const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
+                const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
+                const float2 a = cadd_rn(fek, fok);
+                const float2 b = csub_rn(fek, fok);
+                if (kk != NC - kk) buf[fft_pad(fft_slot_of_input<NC>(kk))] = a;
+                buf[fft_pad(fft_slot_of_input<NC>(NC - kk))] = make_float2(b.x, -b.y);
+            }
+        }
+    }
+    frame_sync<T>(group);
+    float2 v[16];
+    if (active) fft_frame<NC, true>(v, buf, t, group, p.tw_inv);
+    else { if (NC > 256) { frame_sync<T>(group); } frame_sync<T>(group); }
+    if (!active) return;
+    // ifftshift + synthesis window (impl.h:183-198, :1052-1056): complex output o holds samples 2o, 2o+1 of the
+    // un-shifted block; they land at (2o + N/2) mod N
+    float *__restrict__ out = g.frames + ((int64_t)row * g.Fr + (k % g.Fr)) * N;
+    const float2 *__restrict__ w2 = (const float2 *)p.window;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int o = fft_out_index<NC>(t, i);
+        const int oc = (o + NC / 2) & (NC - 1);
+        const float2 w = __ldg(&w2[oc]);
+        ((float2 *)out)[oc] = make_float2(v[i].x * w.x, v[i].y * w.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_overlap_add: one CTA per (slice, row).  The accumulator of the reference receives frames in slice
 // order starting from zero, so summing the covering frames in slice order is the same float sequence.
 // ------------------------------------------------------------------------------------------------
@@ -504,7 +654,22 @@ cudaError_t configure_kernels() {
     return cudaSuccess;
 }
 
+template <int N> static void launch_analyse_t(const DevPlan &p, const DevRows &g, long k0, int nframes, cudaStream_t st) {
+    using S = FftShape<N / 2>;
+    constexpr int T = S::kThreads, G = (T >= 256) ? 1 : 256 / T;
+    const int total = nframes * g.rows;
+    k_analyse_t<N><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, k0, nframes, total);
+}
+
 void launch_analyse(const DevPlan &p, const DevRows &g, long k0, int nframes, cudaStream_t st) {
+    switch (p.N) {
+        case 512: return launch_analyse_t<512>(p, g, k0, nframes, st);
+        case 1024: return launch_analyse_t<1024>(p, g, k0, nframes, st);
+        case 2048: return launch_analyse_t<2048>(p, g, k0, nframes, st);
+        case 4096: return launch_analyse_t<4096>(p, g, k0, nframes, st);
+        case 8192: return launch_analyse_t<8192>(p, g, k0, nframes, st);
+        default: break;
+    }
     dim3 grid(nframes, g.rows);
     k_analyse<<<grid, fft_threads(p), smem_analyse(p), st>>>(p, g, k0);
 }
@@ -529,7 +694,23 @@ void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table, 
     k_fixed_phase<<<grid, 256, 0, st>>>(p, g, table, k0);
 }
 
+template <int N>
+static void launch_synthesise_t(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase, long k0, int nframes, cudaStream_t st) {
+    using S = FftShape<N / 2>;
+    constexpr int T = S::kThreads, G = (T >= 256) ? 1 : 256 / T;
+    const int total = nframes * g.rows;
+    k_synthesise_t<N><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
+}
+
 void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase, long k0, int nframes, cudaStream_t st) {
+    switch (p.N) {
+        case 512: return launch_synthesise_t<512>(p, g, car_mag, car_phase, k0, nframes, st);
+        case 1024: return launch_synthesise_t<1024>(p, g, car_mag, car_phase, k0, nframes, st);
+        case 2048: return launch_synthesise_t<2048>(p, g, car_mag, car_phase, k0, nframes, st);
+        case 4096: return launch_synthesise_t<4096>(p, g, car_mag, car_phase, k0, nframes, st);
+        case 8192: return launch_synthesise_t<8192>(p, g, car_mag, car_phase, k0, nframes, st);
+        default: break;
+    }
     dim3 grid(nframes, g.rows);
     k_synthesise<<<grid, fft_threads(p), smem_synthesise(p), st>>>(p, g, car_mag, car_phase, k0);
 }

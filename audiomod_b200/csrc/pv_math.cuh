@@ -135,3 +135,54 @@ PV_HD float pv_atan2f(float y, float x) {
         default: return PV_SUB(PV_SUB(z, pi_lo), pi);
     }
 }
+
+// Same function, arranged for SIMT: the common case (finite, non-zero arguments, x != 1, exponents within 2^60 of each
+// other, |y/x| < 2^25) runs without data-dependent branches -- the range reduction is written as
+// (a*z + b) / (c*z + d) with per-range constants, which performs exactly the reference's operations
+// (2z-1)/(2+z), (z-1)/(z+1), (z-1.5)/(1+1.5z), -1/z because multiplying by 0, 1 or 2 and adding 0 are exact.
+// Everything else falls through to pv_atan2f above.
+PV_HD float pv_atan2f_fast(float y, float x) {
+    const int32_t hx = PV_F2I(x), hy = PV_F2I(y);
+    const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    const int k = (iy - ix) >> 23;
+    // iy-1 / ix-1 as unsigned: rejects zero and inf/NaN with one compare each
+    const bool common = ((uint32_t)(iy - 1) < 0x7f7fffffu) & ((uint32_t)(ix - 1) < 0x7f7fffffu) & (hx != 0x3f800000) & (k <= 60) & (k >= -60);
+    if (!common) return pv_atan2f(y, x);
+    const float q = PV_I2F(PV_F2I(PV_DIV(y, x)) & 0x7fffffff);  // fabsf(y/x)
+    const int32_t iq = PV_F2I(q);
+    if (iq >= 0x4c000000) return pv_atan2f(y, x);                // |y/x| >= 2^25 (or the quotient overflowed)
+    float a, b, c, d, hi, lo;
+    if (iq < 0x3f300000) {          // < 11/16   (also covers < 7/16, where these are unused)
+        a = 2.0f; b = -1.0f; c = 1.0f; d = 2.0f; hi = PV_I2F(0x3eed6338); lo = PV_I2F(0x31ac3769);
+    } else if (iq < 0x3f980000) {   // < 19/16
+        a = 1.0f; b = -1.0f; c = 1.0f; d = 1.0f; hi = PV_I2F(0x3f490fda); lo = PV_I2F(0x33222168);
+    } else if (iq < 0x401c0000) {   // < 39/16
+        a = 1.0f; b = -1.5f; c = 1.5f; d = 1.0f; hi = PV_I2F(0x3f7b985e); lo = PV_I2F(0x33140fb4);
+    } else {
+        a = 0.0f; b = -1.0f; c = 1.0f; d = 0.0f; hi = PV_I2F(0x3fc90fda); lo = PV_I2F(0x33a22168);
+    }
+    const bool small = iq < 0x3ee00000;  // < 7/16: no reduction
+    const float red = PV_DIV(PV_ADD(PV_MUL(a, q), b), PV_ADD(PV_MUL(c, q), d));
+    const float t = small ? q : red;
+    const float a0 = PV_I2F(0x3eaaaaab), a1 = PV_I2F(0xbe4ccccd), a2 = PV_I2F(0x3e124925), a3 = PV_I2F(0xbde38e38),
+                a4 = PV_I2F(0x3dba2e6e), a5 = PV_I2F(0xbd9d8795), a6 = PV_I2F(0x3d886b35), a7 = PV_I2F(0xbd6ef16b),
+                a8 = PV_I2F(0x3d4bda59), a9 = PV_I2F(0xbd15a221), a10 = PV_I2F(0x3c8569d7);
+    const float z = PV_MUL(t, t);
+    const float w = PV_MUL(z, z);
+    const float s1 = PV_MUL(z, PV_ADD(a0, PV_MUL(w, PV_ADD(a2, PV_MUL(w, PV_ADD(a4, PV_MUL(w, PV_ADD(a6, PV_MUL(w, PV_ADD(a8, PV_MUL(w, a10)))))))))));
+    const float s2 = PV_MUL(w, PV_ADD(a1, PV_MUL(w, PV_ADD(a3, PV_MUL(w, PV_ADD(a5, PV_MUL(w, PV_ADD(a7, PV_MUL(w, a9)))))))));
+    const float ts = PV_MUL(t, PV_ADD(s1, s2));
+    float zr;
+    if (small) {
+        // |t| < 2^-29 returns t unchanged in the reference; t - t*(s1+s2) rounds to t there as well, except that the
+        // reference skips the arithmetic -- identical values for every non-zero t (t is non-zero here)
+        zr = iq < 0x31000000 ? t : PV_SUB(t, ts);
+    } else {
+        zr = PV_SUB(hi, PV_SUB(PV_SUB(ts, lo), t));
+    }
+    const float pi = PV_I2F(0x40490fdb), pi_lo = PV_I2F(0xb3bbbd2e);
+    // the (hx < 0 && k < -60) shortcut of the reference is excluded by `common`
+    if (hx >= 0) return hy < 0 ? -zr : zr;
+    const float zl = PV_SUB(zr, pi_lo);
+    return hy < 0 ? PV_SUB(zl, pi) : PV_SUB(pi, zl);
+}

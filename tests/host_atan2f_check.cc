@@ -19,7 +19,8 @@ static inline uint32_t bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; 
 static inline float fromb(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static long bad = 0, total = 0;
 static inline void check(float y, float x) {
-    float a = pv_atan2f(y, x), b = atan2f(y, x);
+    float a = pv_atan2f(y, x), b = atan2f(y, x), f = pv_atan2f_fast(y, x);
+    if (bits(f) != bits(a) && !(f != f && a != a)) { if (bad < 20) printf("FAST MISMATCH y=%a x=%a fast=%a ref=%a\n", y, x, f, a); ++bad; }
     ++total;
     if (bits(a) != bits(b) && !(a != a && b != b)) {
         if (bad < 20) printf("MISMATCH y=%a x=%a mine=%a (%08x) libm=%a (%08x)\n", y, x, a, bits(a), b, bits(b));
