@@ -97,6 +97,8 @@ struct Pipeline {
     DevBuf b_recs, b_norm, b_whisper, b_carmag, b_carph;
     long recs_base = 0, recs_count = 0;
     int64_t norm_base = 0;
+    int max_consumed = 1;   // largest per-slice contribution to the normalised stream seen so far
+    int ola_run = 16;       // slices per CTA of k_ola_resample
     int64_t launches = 0;
     // optional per-kernel timing with CUDA events on the launching stream
     bool profile = false;
@@ -191,6 +193,7 @@ struct Pipeline {
         recs_base = s.recs_base();
         recs_count = (long)recs.size();
         norm_base = s.norm_base();
+        for (const SliceRec &r : recs) max_consumed = std::max(max_consumed, std::max(r.consumed, r.shift_inc));
         return PVGPU_OK;
     }
 
@@ -220,26 +223,26 @@ struct Pipeline {
         sp = span_begin(2, st);
         launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st);
         span_end(sp, st); ++launches;
-        sp = span_begin(3, st); launch_overlap_add(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, st); span_end(sp, st); ++launches;
-        if (p.rs_active) { sp = span_begin(4, st); launch_resample(p, g, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches; }
+        sp = span_begin(3, st);
+        launch_ola_resample(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, ola_run, max_consumed, st);
+        span_end(sp, st); ++launches;
     }
 };
 
 // Device workspace for a group of rows.
 struct Workspace {
-    DevBuf mag, phase, frames, res, prev_phase, prev_out, peaks, first, n_in, n_out;
+    DevBuf mag, phase, frames, prev_phase, prev_out, peaks, first, n_in, n_out;
     int rows = 0, F = 0, Fr = 0;
-    int64_t res_stride = 0;
 
-    int ensure(const Pipeline &pl, int rows_, int F_, int halo, int64_t res_len) {
+    // halo: frames before the current chunk that the overlap-add of the chunk (and of the resampler history before
+    // it) still reads
+    int ensure(const Pipeline &pl, int rows_, int F_, int halo) {
         const DevPlan &p = pl.p;
         rows = rows_; F = F_; Fr = F_ + halo;
-        res_stride = (res_len + 3) & ~(int64_t)3;
         const int streams = rows / pl.d.cfg.channels;
         CU(mag.ensure(sizeof(float) * (size_t)rows * F * p.Hp));
         CU(phase.ensure(sizeof(float) * (size_t)rows * F * p.Hp));
         CU(frames.ensure(sizeof(float) * (size_t)rows * Fr * p.N));
-        if (p.rs_active) CU(res.ensure(sizeof(float) * (size_t)rows * res_stride));
         CU(prev_phase.ensure(sizeof(float) * (size_t)rows * p.half));
         CU(prev_out.ensure(sizeof(float) * (size_t)rows * p.half));
         CU(peaks.ensure(sizeof(int) * (size_t)streams * (1 + pl.max_peaks())));
@@ -262,15 +265,21 @@ struct Workspace {
     void bind(const Pipeline &pl, DevRows &g) const {
         g.mag = mag.as<float>(); g.phase = phase.as<float>(); g.F = F;
         g.frames = frames.as<float>(); g.Fr = Fr;
-        g.res = res.as<float>(); g.res_stride = res_stride; g.res_base = 0;
         g.prev_phase = prev_phase.as<float>(); g.prev_out = prev_out.as<float>();
         g.peaks = peaks.as<int>(); g.maxpk = pl.max_peaks(); g.first_flag = first.as<int>();
     }
 };
 
-static int halo_of(const std::vector<SliceRec> &recs, long recs_base) {
+// Frames before slice k that k_ola_resample reads when it produces slice k: the frames overlapping k (back to jlo) and,
+// with a resampler, those overlapping the slices that hold its filt_len-1 samples of history.
+static int halo_of(const std::vector<SliceRec> &recs, long recs_base, int hist_len) {
     long h = 1;
-    for (size_t i = 0; i < recs.size(); ++i) h = std::max(h, recs_base + (long)i - recs[i].jlo + 1);
+    for (size_t i = 0; i < recs.size(); ++i) {
+        size_t kh = i;
+        const int64_t u_lo = recs[i].res_off + recs[i].rs_last - hist_len + 1;
+        while (kh > 0 && recs[kh].res_off > u_lo) --kh;
+        h = std::max(h, recs_base + (long)i - recs[kh].jlo + 1);
+    }
     return (int)h;
 }
 
@@ -394,7 +403,9 @@ int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_
     b->n_slices = mp.n_slices;
     b->res_total = main_sched.res_total();
     b->out_total = main_sched.total_out();
-    b->halo = halo_of(main_sched.recs(), main_sched.recs_base());
+    b->halo = halo_of(main_sched.recs(), main_sched.recs_base(), pl.p.rs_active ? (int)pl.p.rs_filt_len : 1);
+    if (b->halo + pl.ola_run > 90) pl.ola_run = std::max(1, 90 - b->halo);
+    if (b->halo + pl.ola_run > 90) return fail(PVGPU_EINVAL, "stretch/pitch ratio too extreme: %d overlapping frames", b->halo);
     int rc;
     if ((rc = pl.upload_schedule(main_sched, nullptr))) return rc;
     if (pl.d.whisper && (rc = pl.build_whisper(b->n_slices))) return rc;
@@ -461,7 +472,7 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
     group = std::max(C, (group / C) * C);
     group = std::min(group, total_rows);
     int rc;
-    if ((rc = b->ws.ensure(b->pl, group, b->frames_per_chunk, b->halo, b->res_total))) return rc;
+    if ((rc = b->ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
     b->pl.launches = 0;
     for (int row0 = 0; row0 < total_rows; row0 += group) {
         const int rows = std::min(group, total_rows - row0);
@@ -636,7 +647,6 @@ struct pvgpu_stream {
     std::vector<std::vector<float>> tail;  // per channel: input samples from in_base on
     std::vector<float> car_tail;
     int64_t in_base = 0;
-    int64_t res_base = 0, res_cap = 0;
     std::vector<std::vector<float>> fifo;  // per channel output FIFO (the reference's outbuf ring)
     size_t fifo_rd = 0;
     int num_res = 0;
@@ -671,29 +681,13 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     const int64_t new_out = sc.total_out() - out_base;
     const int64_t out_stride = std::max<int64_t>((new_out + 3) & ~(int64_t)3, 4);
     CU(s->d_out.ensure(sizeof(float) * (size_t)C * out_stride));
-    if (halo_of(sc.recs(), sc.recs_base()) > s->ws.Fr - s->ws.F) return fail(PVGPU_ESTATE, "too many overlapping (dropped) slices; retrieve output more often");
-    // resampler input stream: keep [res_base, res_total) resident, grow preserving the contents
-    if (p.rs_active) {
-        const int64_t need = sc.res_total() - s->res_base + 8;
-        if (need > s->res_cap) {
-            const int64_t ncap = std::max<int64_t>(need * 2, 1 << 16);
-            DevBuf nb;
-            CU(nb.ensure(sizeof(float) * (size_t)C * ncap));
-            CU(cudaMemsetAsync(nb.p, 0, sizeof(float) * (size_t)C * ncap, s->st));
-            if (s->res_cap) CU(cudaMemcpy2DAsync(nb.p, sizeof(float) * ncap, s->ws.res.p, sizeof(float) * s->res_cap, sizeof(float) * s->res_cap, C, cudaMemcpyDeviceToDevice, s->st));
-            CU(cudaStreamSynchronize(s->st));
-            std::swap(s->ws.res.p, nb.p);
-            std::swap(s->ws.res.bytes, nb.bytes);
-            s->res_cap = ncap;
-        }
-    }
+    if (halo_of(sc.recs(), sc.recs_base(), p.rs_active ? (int)p.rs_filt_len : 1) > s->ws.Fr - s->ws.F) return fail(PVGPU_ESTATE, "too many overlapping (dropped) slices; retrieve output more often");
     DevRows g{};
     g.rows = C; g.channels = C;
     g.in = s->d_in.as<float>(); g.in_stride = in_stride; g.in_base = s->in_base;
     g.n_in = s->d_len.as<int64_t>(); g.n_out = s->d_len.as<int64_t>() + C;
     g.out = s->d_out.as<float>(); g.out_stride = out_stride; g.out_base = out_base;
     s->ws.bind(pl, g);
-    g.res_stride = s->res_cap; g.res_base = s->res_base;
     g.aux_base = k0;
     if (pl.d.whisper) {
         const size_t n = (size_t)added * C * p.H;
@@ -731,16 +725,14 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     for (int c = 0; c < C; ++c) s->tail[c].erase(s->tail[c].begin(), s->tail[c].begin() + dropn);
     if (pl.d.vocoder) s->car_tail.erase(s->car_tail.begin(), s->car_tail.begin() + std::min<int64_t>(dropn, (int64_t)s->car_tail.size()));
     s->in_base += dropn;
-    sc.trim(sc.recs().back().jlo, sc.ola_total());
-    if (p.rs_active) {
-        const int64_t L = p.rs_filt_len;
-        if (sc.res_total() - s->res_base > std::max<int64_t>(4 * L, s->res_cap / 2)) {
-            const int64_t keep_from = sc.res_total() - L;  // later taps start at res_off + last - L + 1 >= res_total - L + 1
-            CU(cudaMemcpy2DAsync(s->ws.res.p, sizeof(float) * s->res_cap, s->ws.res.as<float>() + (keep_from - s->res_base), sizeof(float) * s->res_cap,
-                                 sizeof(float) * L, C, cudaMemcpyDeviceToDevice, s->st));
-            CU(cudaStreamSynchronize(s->st));
-            s->res_base = keep_from;
-        }
+    {
+        // keep every record / normaliser a later slice can still reach: the slices holding the last filt_len-1 samples of
+        // the normalised stream (resampler history) and the frames overlapping them
+        const auto &recs = sc.recs();
+        const int64_t L = p.rs_active ? (int64_t)p.rs_filt_len : 1;
+        size_t kh = recs.size() - 1;
+        while (kh > 0 && recs[kh].res_off > sc.res_total() - L) --kh;
+        sc.trim(recs[kh].jlo, recs[kh].ola_off);
     }
     return PVGPU_OK;
 }
@@ -760,8 +752,9 @@ int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out) {
     s->tail.resize(cfg->channels);
     s->fifo.resize(cfg->channels);
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
-    const int halo = std::max(64, 4 * s->pl.d.N / std::max(1, s->pl.d.hop));
-    if ((rc = s->ws.ensure(s->pl, cfg->channels, pvgpu_stream::kF, halo, 0))) return rc;
+    const int halo = 80;
+    s->pl.ola_run = 8;
+    if ((rc = s->ws.ensure(s->pl, cfg->channels, pvgpu_stream::kF, halo))) return rc;
     if ((rc = s->ws.reset_state(s->pl, s->st))) return rc;
     *out = s.release();
     return PVGPU_OK;

@@ -548,74 +548,161 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_overlap_add: one CTA per (slice, row).  The accumulator of the reference receives frames in slice
-// order starting from zero, so summing the covering frames in slice order is the same float sequence.
+// k_ola_resample: overlap-add + window-sum normalisation (+ the Speex resampler for pitch modes), one CTA per
+// (run of consecutive slices, row).
+//
+// The accumulator of the reference receives frames in slice order starting from zero (:1057-1073) and its first
+// shift_k samples are final after slice k (:1152,1185-1190), so position t of the normalised stream is the sum, in slice
+// order, of the frames covering t, divided by the data-independent window sum norm[t].  The CTA first builds that stream
+// for the span its outputs need (the run's own samples plus the filt_len-1 samples of resampler history before it) in
+// shared memory, then either stores it (no resampling) or runs the windowed-sinc interpolation from shared memory
+// (resample.c:462-560: four accumulators over filt_len taps, cubic interpolation between table phases).  The sinc table
+// is staged as "quads" q[e] = (tab[e-2], tab[e-1], tab[e], tab[e+1]) so one 128-bit shared load feeds the four FMAs.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_overlap_add(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
-                              int64_t norm_base, long recs_base, long k0) {
+constexpr int kOlaMaxSlices = 48;   // run + history slices held in the CTA's tables
+constexpr int kOlaMaxFrames = 96;   // frames overlapping them
+
+struct OlaTables {
+    int64_t res_off[kOlaMaxSlices + 1];   // resampler-stream offset of each table slice (+ end sentinel)
+    int64_t ola_off[kOlaMaxSlices];
+    int jlo[kOlaMaxSlices];
+    int fr_off[kOlaMaxFrames];            // ola_off of frame (jmin + i) relative to ola_base
+    int fr_slot[kOlaMaxFrames];           // its slot in the frame ring
+    int out_pref[kOlaMaxSlices + 1];      // flattened output index of each run slice
+    long kmin, jmin;
+    int nsl, nfr;
+    int64_t ola_base, u_lo, u_hi;
+};
+
+__global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
+                                                      int64_t norm_base, long recs_base, long k0, int nf, int run, int max_in) {
+    extern __shared__ float4 smem4[];
+    __shared__ OlaTables T;
     const int row = blockIdx.y;
-    const long k = k0 + blockIdx.x;
-    const SliceRec r = recs[k - recs_base];
-    if (r.flags & 1) return;  // dropped slice: accumulated (by later gathers), nothing written
+    const long ka = k0 + (long)blockIdx.x * run;
+    const long kb = min(ka + run, k0 + (long)nf);
+    const int L = p.rs_active ? (int)p.rs_filt_len : 1;
+    const bool quad = p.rs_active && !p.rs_direct;
+    float4 *s_quad = smem4;
+    float *s_in = (float *)(smem4 + (quad ? p.rs_table_len : 0));
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        // slices whose normalised samples are needed: the run plus the resampler history before it
+        const SliceRec &ra = recs[ka - recs_base];
+        const int64_t u_lo = p.rs_active ? ra.res_off + ra.rs_last - L + 1 : ra.res_off;
+        long kmin = ka;
+        while (kmin > recs_base && kmin > 0 && recs[kmin - recs_base].res_off > u_lo && ka - kmin < kOlaMaxSlices - run - 1) --kmin;
+        int n = 0, pref = 0;
+        long jmin = recs[kmin - recs_base].jlo;
+        for (long k = kmin; k < kb; ++k, ++n) {
+            const SliceRec &r = recs[k - recs_base];
+            T.res_off[n] = r.res_off;
+            T.ola_off[n] = r.ola_off;
+            T.jlo[n] = r.jlo;
+            if (k >= ka) {
+                T.out_pref[k - ka] = pref;
+                int n_store = (r.flags & 1) ? 0 : r.n_write;
+                if (r.out_off + n_store > g.n_out[row]) n_store = (int)max((int64_t)0, g.n_out[row] - r.out_off);
+                pref += n_store;
+            }
+        }
+        T.out_pref[kb - ka] = pref;
+        const SliceRec &rl = recs[kb - 1 - recs_base];
+        const int64_t u_hi = rl.res_off + ((rl.flags & 1) ? 0 : rl.consumed);
+        T.res_off[n] = u_hi;
+        T.kmin = kmin; T.jmin = jmin; T.nsl = n;
+        T.ola_base = recs[jmin - recs_base].ola_off;
+        int nfr = (int)(kb - jmin);
+        if (nfr > kOlaMaxFrames) nfr = kOlaMaxFrames;   // cannot happen for schedules the host accepts (halo check)
+        T.nfr = nfr;
+        T.u_lo = u_lo < 0 ? 0 : u_lo;
+        T.u_hi = u_hi;
+    }
+    __syncthreads();
+    for (int i = tid; i < T.nfr; i += blockDim.x) {
+        const long j = T.jmin + i;
+        T.fr_off[i] = (int)(recs[j - recs_base].ola_off - T.ola_base);
+        T.fr_slot[i] = (int)(j % g.Fr);
+    }
+    if (quad) {
+        const float *__restrict__ tab = p.rs_table;
+        for (int e = tid; e < p.rs_table_len; e += blockDim.x) {
+            const float a = e >= 2 ? tab[e - 2] : 0.f, b = e >= 1 ? tab[e - 1] : 0.f, c = tab[e], d = e + 1 < p.rs_table_len ? tab[e + 1] : 0.f;
+            s_quad[e] = make_float4(a, b, c, d);
+        }
+    }
+    __syncthreads();
+
+    // ---- normalised overlap-add stream for [u_lo, u_hi) ----
     const int N = p.N;
     const float *__restrict__ fr = g.frames + (int64_t)row * g.Fr * N;
-    for (int i = threadIdx.x; i < r.shift_inc; i += blockDim.x) {
-        const int64_t t = r.ola_off + i;
+    const int64_t u_lo = T.u_lo, u_hi = T.u_hi;
+    const int span = (int)min(u_hi - u_lo, (int64_t)max_in);
+    const int nsl = T.nsl;
+    const int64_t row_out = (int64_t)row * g.out_stride - g.out_base;
+    for (int e = tid; e < span; e += blockDim.x) {
+        const int64_t u = u_lo + e;
+        int lo = 0, hi = nsl;   // last table slice with res_off <= u (dropped / empty slices share an offset: take the last)
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (T.res_off[mid] <= u) lo = mid; else hi = mid; }
+        const int64_t t = T.ola_off[lo] + (u - T.res_off[lo]);
+        const int trel = (int)(t - T.ola_base);
+        const int j0 = (int)(T.jlo[lo] - T.jmin), j1 = (int)(T.kmin + lo - T.jmin);
         float acc = 0.f;
-        for (long j = r.jlo; j <= k; ++j) {
-            const int64_t off = t - recs[j - recs_base].ola_off;
-            if (off < N) acc += fr[(j % g.Fr) * N + off];
+        for (int j = j0; j <= j1; ++j) {
+            const int off = trel - T.fr_off[j];
+            if (off < N) acc += fr[(int64_t)T.fr_slot[j] * N + off];
         }
         const float v = acc / norm[t - norm_base];
         if (p.rs_active) {
-            if (i < r.consumed) g.res[(int64_t)row * g.res_stride + (r.res_off + i - g.res_base)] = v;
-        } else if (i < r.n_write && r.out_off + i < g.n_out[row]) {
-            g.out[(int64_t)row * g.out_stride + (r.out_off + i - g.out_base)] = v;
+            s_in[e] = v;
+        } else {
+            // no resampling: res_off == out_off and the sample goes straight out (n_write / n_out clip)
+            const int ks = (int)(T.kmin + lo - ka);
+            if (ks >= 0) {
+                const int i = (int)(u - T.res_off[lo]);
+                if (i < T.out_pref[ks + 1] - T.out_pref[ks]) g.out[row_out + recs[ka + ks - recs_base].out_off + i] = v;
+            }
         }
     }
-}
+    if (!p.rs_active) return;
+    __syncthreads();
 
-// ------------------------------------------------------------------------------------------------
-// k_resample: one CTA per (slice, row); one thread per output sample
-// ------------------------------------------------------------------------------------------------
-__global__ void k_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base, long k0) {
-    const int row = blockIdx.y;
-    const long k = k0 + blockIdx.x;
-    const SliceRec r = recs[k - recs_base];
-    if (r.flags & 1) return;
-    const int L = (int)p.rs_filt_len;
-    const float *__restrict__ x = g.res + (int64_t)row * g.res_stride;
-    const float *__restrict__ tab = p.rs_table;
-    int n_store = r.n_write;
-    if (r.out_off + n_store > g.n_out[row]) n_store = (int)max((int64_t)0, g.n_out[row] - r.out_off);
-    for (int i = threadIdx.x; i < n_store; i += blockDim.x) {
+    // ---- resampler: flattened outputs of the run ----
+    const int total_out = T.out_pref[kb - ka];
+    const int nrun = (int)(kb - ka);
+    const int ov = (int)p.rs_oversample;
+    for (int e = tid; e < total_out; e += blockDim.x) {
+        int ks = 0;
+        while (ks + 1 < nrun && T.out_pref[ks + 1] <= e) ++ks;
+        const int i = e - T.out_pref[ks];
+        const SliceRec &r = recs[ka + ks - recs_base];
         // position of output i: i steps of (int_advance, frac_advance) with carry (resample.c:548-554)
-        const uint64_t fr = (uint64_t)r.rs_frac + (uint64_t)i * (uint64_t)p.rs_frac_adv;
-        const int last = r.rs_last + i * p.rs_int_adv + (int)(fr / p.rs_den);
-        const uint32_t frac_num = (uint32_t)(fr % p.rs_den);
-        const int64_t pos0 = r.res_off + last - L + 1;  // global resampler-input position of tap 0
+        const uint64_t fq = (uint64_t)r.rs_frac + (uint64_t)i * (uint64_t)p.rs_frac_adv;
+        const int last = r.rs_last + i * p.rs_int_adv + (int)(fq / p.rs_den);
+        const uint32_t frac_num = (uint32_t)(fq % p.rs_den);
+        const int64_t pos0 = r.res_off + last - L + 1;   // resampler-stream position of tap 0 (negative: zero history)
+        int jbeg = 0;
+        if (pos0 < u_lo) jbeg = (int)min((int64_t)L, u_lo - pos0);   // only at the very start of a stream (u_lo clipped to 0)
+        const float *xs = s_in + (pos0 - u_lo);
         float sum;
         if (p.rs_direct) {
             sum = 0.f;
-            const float *t = tab + (size_t)frac_num * L;
-            for (int j = 0; j < L; ++j) {
-                const int64_t q = pos0 + j;
-                const float v = q >= 0 ? x[q - g.res_base] : 0.f;
-                sum += v * t[j];
-            }
+            const float *__restrict__ tt = p.rs_table + (size_t)frac_num * L;
+            for (int j = jbeg; j < L; ++j) sum += xs[j] * __ldg(&tt[j]);
         } else {
-            const uint32_t ov = p.rs_oversample;
-            const int offset = (int)(frac_num * ov / p.rs_den);
-            const float frac = ((float)((frac_num * ov) % p.rs_den)) / p.rs_den;
+            const int offset = (int)(frac_num * (uint32_t)ov / p.rs_den);
+            const float frac = ((float)((frac_num * (uint32_t)ov) % p.rs_den)) / p.rs_den;
+            const float4 *q = s_quad + 4 + ov - offset;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            for (int j = 0; j < L; ++j) {
-                const int64_t q = pos0 + j;
-                const float v = q >= 0 ? x[q - g.res_base] : 0.f;
-                const float *t = tab + 4 + (j + 1) * (int)ov - offset;
-                a0 += v * t[-2];
-                a1 += v * t[-1];
-                a2 += v * t[0];
-                a3 += v * t[1];
+#pragma unroll 8
+            for (int j = jbeg; j < L; ++j) {
+                const float v = xs[j];
+                const float4 tq = q[j * ov];
+                a0 += v * tq.x;
+                a1 += v * tq.y;
+                a2 += v * tq.z;
+                a3 += v * tq.w;
             }
             // cubic_coef (resample.c:339-351)
             const float i0 = -0.16667f * frac + 0.16667f * frac * frac * frac;
@@ -624,7 +711,7 @@ __global__ void k_resample(const DevPlan p, const DevRows g, const SliceRec *__r
             const float i2 = (float)(1. - i0 - i1 - i3);
             sum = (i0 * a0) + (i1 * a1) + (i2 * a2) + (i3 * a3);
         }
-        g.out[(int64_t)row * g.out_stride + (r.out_off + i - g.out_base)] = sum;
+        g.out[row_out + r.out_off + i] = sum;
     }
 }
 
@@ -649,6 +736,7 @@ cudaError_t configure_kernels() {
     const int big = 200 * 1024;
     if ((e = cudaFuncSetAttribute(k_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_synthesise, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -715,15 +803,16 @@ void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag,
     k_synthesise<<<grid, fft_threads(p), smem_synthesise(p), st>>>(p, g, car_mag, car_phase, k0);
 }
 
-void launch_overlap_add(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
-                        long k0, int nframes, cudaStream_t st) {
-    dim3 grid(nframes, g.rows);
-    k_overlap_add<<<grid, 128, 0, st>>>(p, g, recs, norm, norm_base, recs_base, k0);
-}
-
-void launch_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
-    dim3 grid(nframes, g.rows);
-    k_resample<<<grid, 128, 0, st>>>(p, g, recs, recs_base, k0);
+void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
+                         long k0, int nframes, int run, int max_consumed, cudaStream_t st) {
+    if (run > kOlaMaxSlices - 16) run = kOlaMaxSlices - 16;
+    if (run < 1) run = 1;
+    const int L = p.rs_active ? (int)p.rs_filt_len : 1;
+    const int max_in = run * max_consumed + L + 8;
+    const bool quad = p.rs_active && !p.rs_direct;
+    const size_t sm = (quad ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)max_in;
+    dim3 grid((nframes + run - 1) / run, g.rows);
+    k_ola_resample<<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in);
 }
 
 }  // namespace pvgpu

@@ -42,8 +42,6 @@ struct DevRows {
     int F;                    // frame slots per row in mag/phase
     float *frames;            // [rows][Fr][N] synthesised frames, slot = frame % Fr
     int Fr;
-    float *res;               // [rows][res_stride] resampler input stream, element 0 is position res_base
-    int64_t res_stride, res_base;
     float *out;               // [rows][out_stride], element 0 is output position out_base
     int64_t out_stride, out_base;
     const int64_t *n_out;     // per row: output positions >= n_out are not stored (truncation to the stream's length)
@@ -60,10 +58,10 @@ void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table /
                         long k0, int nframes, cudaStream_t st);
 void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase /*[slices][Hp] indexed by absolute slice, or null*/,
                        long k0, int nframes, cudaStream_t st);
-void launch_overlap_add(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base,
-                        long recs_base, long k0, int nframes, cudaStream_t st);
-void launch_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st);
-
+// overlap-add + normalisation (+ resampler when p.rs_active); `run` consecutive slices per CTA, max_consumed = the largest
+// number of normalised samples any slice contributes
+void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
+                         long k0, int nframes, int run, int max_consumed, cudaStream_t st);
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
 

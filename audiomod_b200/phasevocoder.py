@@ -173,7 +173,7 @@ class PhaseVocoderBatch:
         self.run_host_rows(in_rows, out_rows)
         return outs
 
-    KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "overlap_add", "resample", "fixed_phase")
+    KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "ola_resample", "unused", "fixed_phase")
 
     def profile(self, enable=True):
         check(_lib.lib().pvgpu_batch_profile(self._h, int(bool(enable))))

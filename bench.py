@@ -257,7 +257,7 @@ def main():
     slices = stats["slices"]
     shift = hop * info["hs_ratio"]
     per_frame = {"analyse": 4 * (hop + 2 * H), "phase_core": 4 * (2 * H + half), "synthesise": 4 * (2 * H + N),
-                 "overlap_add": 4 * (N + shift), "resample": 4 * (shift + shift / info["pitch_scale"])}
+                 "ola_resample": 4 * (N + shift / info["pitch_scale"])}
     dom = max((k for k in per_frame if ktimes[k][1] > 0), key=lambda k: ktimes[k][0])
     dom_ms, dom_launches = ktimes[dom]
     bytes_total = per_frame[dom] * slices * S * args.steps

@@ -112,7 +112,7 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
 int pvgpu_batch_stats(const pvgpu_batch *b, int64_t *kernel_launches, int64_t *slices, int64_t *h2d_bytes, int64_t *d2h_bytes);
 int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);
 /* Per-kernel device timing with CUDA events recorded on the launching stream around every launch.  kinds:
- * 0 analyse, 1 phase core, 2 synthesise, 3 overlap-add, 4 resample, 5 fixed phase (robotic/whisper).
+ * 0 analyse, 1 phase core, 2 synthesise, 3 overlap-add + resample, 5 fixed phase (robotic/whisper).
  * pvgpu_batch_kernel_times synchronises the device and returns the totals since profiling was enabled. */
 enum { PVGPU_KINDS = 8 };
 int pvgpu_batch_profile(pvgpu_batch *b, int enable);
