@@ -57,7 +57,7 @@ SYMBOLS = {
     "pvgpu_batch_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
     "pvgpu_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "pvgpu_batch_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i64p]),
-    "pvgpu_batch_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "pvgpu_batch_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "pvgpu_test_forward_polar": (C.c_int, [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "pvgpu_test_inverse_polar": (C.c_int, [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "pvgpu_test_atan2f": (C.c_int, [C.c_int, C.c_int64, _fp, _fp, _fp]),

@@ -8,7 +8,7 @@
 // The object layout (two vptrs, then the private block starting with the engine pointer) is kept identical to the
 // reference's so that objects allocated by callers compiled against the reference header have the right size; when
 // the reference headers are on the include path the shim can be built against them directly with
-// -DPVGPU_DROPIN_USE_REFERENCE_HEADERS (that is what oracle/Makefile's `gpu-exe` target does).
+// -DPVGPU_DROPIN_USE_REFERENCE_HEADERS.
 #pragma once
 
 #ifdef PVGPU_DROPIN_USE_REFERENCE_HEADERS

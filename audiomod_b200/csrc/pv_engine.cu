@@ -256,9 +256,7 @@ struct Workspace {
         CU(cudaMemsetAsync(prev_phase.p, 0, sizeof(float) * (size_t)rows * p.half, st));
         CU(cudaMemsetAsync(prev_out.p, 0, sizeof(float) * (size_t)rows * p.half, st));
         CU(cudaMemsetAsync(peaks.p, 0, sizeof(int) * (size_t)streams * (1 + pl.max_peaks()), st));
-        std::vector<int> ones(streams, 1);
-        CU(cudaMemcpyAsync(first.p, ones.data(), sizeof(int) * streams, cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));  // `ones` is a temporary
+        CU(cudaMemsetAsync(first.p, 0, sizeof(int) * (size_t)streams, st));
         return PVGPU_OK;
     }
 
@@ -266,7 +264,7 @@ struct Workspace {
         g.mag = mag.as<float>(); g.phase = phase.as<float>(); g.F = F;
         g.frames = frames.as<float>(); g.Fr = Fr;
         g.prev_phase = prev_phase.as<float>(); g.prev_out = prev_out.as<float>();
-        g.peaks = peaks.as<int>(); g.maxpk = pl.max_peaks(); g.first_flag = first.as<int>();
+        g.peaks = peaks.as<int>(); g.maxpk = pl.max_peaks(); g.started = first.as<int>();
     }
 };
 
@@ -301,11 +299,33 @@ struct pvgpu_batch {
     int halo = 1;
     int64_t res_total = 0, out_total = 0;
     int frames_per_chunk = 64, rows_per_group = 0;
-    Workspace ws;
-    DevBuf d_nin, d_nout, d_stage_in, d_stage_out;
+    // Groups of rows are processed round-robin on a few contexts (stream + workspace + staging buffers) so that the
+    // serial-in-time phase kernel of one group overlaps the FFT kernels of another, and -- for host buffers -- H2D,
+    // kernels and D2H of different groups overlap.
+    struct Ctx {
+        cudaStream_t st = nullptr;
+        cudaEvent_t done = nullptr;
+        Workspace ws;
+        DevBuf stage_in, stage_out;
+    };
+    static constexpr int kCtx = 4;
+    int n_contexts = 3;
+    Ctx ctx[kCtx];
+    cudaEvent_t ev_fork = nullptr;
+    DevBuf d_nin, d_nout;
     cudaStream_t stream = nullptr;
     int64_t h2d = 0, d2h = 0;
-    ~pvgpu_batch() { if (stream) cudaStreamDestroy(stream); }
+    ~pvgpu_batch() {
+        for (auto &c : ctx) { if (c.st) cudaStreamDestroy(c.st); if (c.done) cudaEventDestroy(c.done); }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    int group_rows() const {
+        const int C = cfg.channels, total = n_streams * C;
+        int group = rows_per_group > 0 ? rows_per_group : 512;
+        group = std::max(C, (group / C) * C);
+        return std::min(group, total);
+    }
 };
 
 extern "C" {
@@ -350,6 +370,11 @@ int pvgpu_batch_create(const pvgpu_config *cfg, int n_streams, int64_t max_in_sa
     b->max_in = max_in_samples;
     if ((rc = b->pl.init(*cfg))) return rc;
     CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+    for (auto &c : b->ctx) {
+        CU(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+    }
     *out = b.release();
     return PVGPU_OK;
 }
@@ -366,10 +391,11 @@ int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info) {
     return PVGPU_OK;
 }
 
-int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group) {
+int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, int contexts) {
     if (!b) return fail(PVGPU_EINVAL, "null batch");
     if (frames_per_chunk > 0) b->frames_per_chunk = frames_per_chunk;
     if (rows_per_group > 0) b->rows_per_group = rows_per_group;
+    if (contexts > 0) b->n_contexts = std::min(contexts, (int)pvgpu_batch::kCtx);
     return PVGPU_OK;
 }
 
@@ -439,22 +465,24 @@ int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_
     return PVGPU_OK;
 }
 
-static int batch_run_group(pvgpu_batch *b, const float *d_in, int64_t in_stride, float *d_out, int64_t out_stride, int row0, int rows,
-                           cudaStream_t st) {
+// One group of rows on one context; everything is enqueued on ctx.st.
+static int batch_run_group(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, const float *d_in, int64_t in_stride, float *d_out, int64_t out_stride,
+                           int row0, int rows) {
     Pipeline &pl = b->pl;
     int rc;
-    if ((rc = b->ws.reset_state(pl, st))) return rc;
+    ctx.ws.rows = rows;
+    if ((rc = ctx.ws.reset_state(pl, ctx.st))) return rc;
     DevRows g{};
     g.rows = rows; g.channels = b->cfg.channels;
-    g.in = d_in + (int64_t)row0 * in_stride; g.in_stride = in_stride; g.in_base = 0;
+    g.in = d_in; g.in_stride = in_stride; g.in_base = 0;
     g.n_in = b->d_nin.as<int64_t>() + row0;
     g.n_out = b->d_nout.as<int64_t>() + row0;
-    g.out = d_out + (int64_t)row0 * out_stride; g.out_stride = out_stride; g.out_base = 0;
-    b->ws.bind(pl, g);
-    const int F = b->ws.F;
+    g.out = d_out; g.out_stride = out_stride; g.out_base = 0;
+    ctx.ws.bind(pl, g);
+    const int F = ctx.ws.F;
     for (long k0 = 0; k0 < b->n_slices; k0 += F) {
         const int nf = (int)std::min<long>(F, b->n_slices - k0);
-        pl.run_frames(g, k0, nf, st);
+        pl.run_frames(g, k0, nf, ctx.st);
     }
     CU(cudaGetLastError());
     return PVGPU_OK;
@@ -466,19 +494,56 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
     if (fmt != PVGPU_F32) return fail(PVGPU_EINVAL, "device runs take float32 rows");
     CU(cudaSetDevice(b->pl.device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
-    const int C = b->cfg.channels;
-    const int total_rows = b->n_streams * C;
-    int group = b->rows_per_group > 0 ? b->rows_per_group : total_rows;
-    group = std::max(C, (group / C) * C);
-    group = std::min(group, total_rows);
+    const int total_rows = b->n_streams * b->cfg.channels;
+    const int group = b->group_rows();
+    const int n_groups = (total_rows + group - 1) / group;
+    const int n_ctx = std::min(n_groups, b->n_contexts);
     int rc;
-    if ((rc = b->ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
+    for (int i = 0; i < n_ctx; ++i)
+        if ((rc = b->ctx[i].ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
     b->pl.launches = 0;
-    for (int row0 = 0; row0 < total_rows; row0 += group) {
-        const int rows = std::min(group, total_rows - row0);
-        if ((rc = batch_run_group(b, (const float *)d_in, in_stride, (float *)d_out, out_stride, row0, rows, st))) return rc;
+    // fork: the contexts start after everything already queued on the caller's stream
+    CU(cudaEventRecord(b->ev_fork, st));
+    for (int i = 0; i < n_ctx; ++i) CU(cudaStreamWaitEvent(b->ctx[i].st, b->ev_fork, 0));
+    for (int gi = 0; gi < n_groups; ++gi) {
+        const int row0 = gi * group, rows = std::min(group, total_rows - row0);
+        if ((rc = batch_run_group(b, b->ctx[gi % n_ctx], (const float *)d_in + (int64_t)row0 * in_stride, in_stride,
+                                  (float *)d_out + (int64_t)row0 * out_stride, out_stride, row0, rows))) return rc;
+    }
+    // join
+    for (int i = 0; i < n_ctx; ++i) {
+        CU(cudaEventRecord(b->ctx[i].done, b->ctx[i].st));
+        CU(cudaStreamWaitEvent(st, b->ctx[i].done, 0));
     }
     if (!cuda_stream) CU(cudaStreamSynchronize(st));
+    return PVGPU_OK;
+}
+
+// rows [r0, r0+rows) between host row pointers and a dense device block; one 2-D copy when the host rows are evenly
+// spaced, one copy per row otherwise
+static int copy_rows(void *dev, int64_t dev_stride, const void *const *host_rows, int r0, int rows, const int64_t *lens, int C, bool to_device,
+                     cudaStream_t st, int64_t *bytes) {
+    bool regular = rows > 1;
+    const ptrdiff_t pitch = rows > 1 ? (const char *)host_rows[r0 + 1] - (const char *)host_rows[r0] : 0;
+    int64_t maxlen = 0;
+    for (int r = 0; r < rows; ++r) {
+        maxlen = std::max(maxlen, lens[(r0 + r) / C]);
+        if (r + 1 < rows && (const char *)host_rows[r0 + r + 1] - (const char *)host_rows[r0 + r] != pitch) regular = false;
+    }
+    if (regular && pitch >= (ptrdiff_t)(maxlen * sizeof(float)) && maxlen > 0) {
+        if (to_device) CU(cudaMemcpy2DAsync(dev, dev_stride * sizeof(float), host_rows[r0], (size_t)pitch, maxlen * sizeof(float), rows, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpy2DAsync((void *)host_rows[r0], (size_t)pitch, dev, dev_stride * sizeof(float), maxlen * sizeof(float), rows, cudaMemcpyDeviceToHost, st));
+        for (int r = 0; r < rows; ++r) *bytes += sizeof(float) * lens[(r0 + r) / C];
+        return PVGPU_OK;
+    }
+    for (int r = 0; r < rows; ++r) {
+        const int64_t n = lens[(r0 + r) / C];
+        if (!n) continue;
+        float *d = (float *)dev + (int64_t)r * dev_stride;
+        if (to_device) CU(cudaMemcpyAsync(d, host_rows[r0 + r], sizeof(float) * n, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpyAsync((void *)host_rows[r0 + r], d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+        *bytes += sizeof(float) * n;
+    }
     return PVGPU_OK;
 }
 
@@ -493,22 +558,28 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
     for (int s = 0; s < b->n_streams; ++s) { in_stride = std::max(in_stride, b->n_in[s]); out_stride = std::max(out_stride, b->n_out[s]); }
     in_stride = std::max<int64_t>((in_stride + 3) & ~(int64_t)3, 4);
     out_stride = std::max<int64_t>((out_stride + 3) & ~(int64_t)3, 4);
-    CU(b->d_stage_in.ensure(sizeof(float) * (size_t)total_rows * in_stride));
-    CU(b->d_stage_out.ensure(sizeof(float) * (size_t)total_rows * out_stride));
+    const int group = b->group_rows();
+    const int n_groups = (total_rows + group - 1) / group;
+    const int n_ctx = std::min(n_groups, b->n_contexts);
+    int rc;
+    for (int i = 0; i < n_ctx; ++i) {
+        pvgpu_batch::Ctx &c = b->ctx[i];
+        if ((rc = c.ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
+        CU(c.stage_in.ensure(sizeof(float) * (size_t)group * in_stride));
+        CU(c.stage_out.ensure(sizeof(float) * (size_t)group * out_stride));
+    }
+    b->pl.launches = 0;
     b->h2d = b->d2h = 0;
-    for (int r = 0; r < total_rows; ++r) {
-        const int64_t n = b->n_in[r / C];
-        if (n) CU(cudaMemcpyAsync(b->d_stage_in.as<float>() + (int64_t)r * in_stride, in_rows[r], sizeof(float) * n, cudaMemcpyHostToDevice, b->stream));
-        b->h2d += sizeof(float) * n;
+    // each context's stream carries H2D -> kernels -> D2H of its groups in order; the contexts run concurrently, so the
+    // copies of one group overlap the kernels of the others
+    for (int gi = 0; gi < n_groups; ++gi) {
+        pvgpu_batch::Ctx &c = b->ctx[gi % n_ctx];
+        const int row0 = gi * group, rows = std::min(group, total_rows - row0);
+        if ((rc = copy_rows(c.stage_in.p, in_stride, in_rows, row0, rows, b->n_in.data(), C, true, c.st, &b->h2d))) return rc;
+        if ((rc = batch_run_group(b, c, c.stage_in.as<float>(), in_stride, c.stage_out.as<float>(), out_stride, row0, rows))) return rc;
+        if ((rc = copy_rows(c.stage_out.p, out_stride, (const void *const *)out_rows, row0, rows, b->n_out.data(), C, false, c.st, &b->d2h))) return rc;
     }
-    int rc = pvgpu_batch_run_device(b, b->d_stage_in.p, in_stride, b->d_stage_out.p, out_stride, fmt, b->stream);
-    if (rc) return rc;
-    for (int r = 0; r < total_rows; ++r) {
-        const int64_t n = b->n_out[r / C];
-        if (n) CU(cudaMemcpyAsync(out_rows[r], b->d_stage_out.as<float>() + (int64_t)r * out_stride, sizeof(float) * n, cudaMemcpyDeviceToHost, b->stream));
-        b->d2h += sizeof(float) * n;
-    }
-    CU(cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < n_ctx; ++i) CU(cudaStreamSynchronize(b->ctx[i].st));
     return PVGPU_OK;
 }
 

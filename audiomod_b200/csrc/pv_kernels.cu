@@ -221,7 +221,7 @@ __global__ void k_phase_core(const DevPlan p, const DevRows g, const SliceRec *_
         }
     }
     int *gpk = g.peaks + (int64_t)stream * (1 + maxpk);
-    if (tid == 0) { s_misc[1] = gpk[0]; s_misc[2] = g.first_flag[stream]; }
+    if (tid == 0) { s_misc[1] = gpk[0]; s_misc[2] = g.started[stream] == 0; }
     __syncthreads();
     for (int i = tid; i < s_misc[1]; i += nthr) s_prev[i] = gpk[1 + i];
     __syncthreads();
@@ -342,7 +342,7 @@ __global__ void k_phase_core(const DevPlan p, const DevRows g, const SliceRec *_
     }
     const int nprev = s_misc[1];
     for (int i = tid; i < nprev; i += nthr) gpk[1 + i] = s_prev[i];
-    if (tid == 0) { gpk[0] = nprev; g.first_flag[stream] = s_misc[2]; }
+    if (tid == 0) { gpk[0] = nprev; g.started[stream] = s_misc[2] ? 0 : 1; }
 }
 
 // coremode 2: phase *= phaseIncrement / hop (two float roundings, :558-572)

@@ -48,7 +48,7 @@ struct DevRows {
     float *prev_phase, *prev_out;   // [rows][half] phase-core state
     int *peaks;               // [streams][1 + maxpk]: count, then previous peak list (shared by a stream's channels)
     int maxpk;
-    int *first_flag;          // [streams] 1 until the first slice of the stream went through the core
+    int *started;             // [streams] 0 until the first slice of the stream went through the core
     long aux_base;            // slice index of element 0 of the whisper table / carrier spectra
 };
 

@@ -138,8 +138,8 @@ class PhaseVocoderBatch:
         check(_lib.lib().pvgpu_batch_info(self._h, C.byref(info)))
         return _info_dict(info)
 
-    def tune(self, frames_per_chunk=0, rows_per_group=0):
-        check(_lib.lib().pvgpu_batch_tune(self._h, int(frames_per_chunk), int(rows_per_group)))
+    def tune(self, frames_per_chunk=0, rows_per_group=0, contexts=0):
+        check(_lib.lib().pvgpu_batch_tune(self._h, int(frames_per_chunk), int(rows_per_group), int(contexts)))
 
     def plan(self, n_in, block: int = 0) -> np.ndarray:
         n_in = np.ascontiguousarray(np.broadcast_to(np.asarray(n_in, dtype=np.int64), (self.n_streams,)))

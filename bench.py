@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-chunk", type=int, default=0)
     ap.add_argument("--rows-per-group", type=int, default=0)
+    ap.add_argument("--contexts", type=int, default=0)
     ap.add_argument("--cpu-streams-per-core", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -217,8 +218,8 @@ def main():
     d_in = torch.zeros((S, stride), dtype=torch.float32, device=dev)
     d_in[:, :n] = make_inputs(torch, dev, S, n, 1234 + rank)
     batch = A.PhaseVocoderBatch(S, n, SR, 1, 1.0, SEMITONES, MODE, COREMODE, FFT, device=local)
-    if args.frames_per_chunk or args.rows_per_group:
-        batch.tune(args.frames_per_chunk, args.rows_per_group)
+    if args.frames_per_chunk or args.rows_per_group or args.contexts:
+        batch.tune(args.frames_per_chunk, args.rows_per_group, args.contexts)
     n_out = batch.plan(n)
     out_stride = (int(n_out.max()) + 3) & ~3
     d_out = torch.zeros((S, out_stride), dtype=torch.float32, device=dev)
@@ -234,7 +235,6 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    batch.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -243,10 +243,24 @@ def main():
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    ktimes = batch.kernel_times()
-    batch.profile(False)
     stats = batch.stats()
     clocks = sampler.summary()
+    # per-kernel CUDA-event times: the same steps once more with one group in flight at a time, so that a kernel's
+    # events bracket only that kernel (with several groups in flight kernels of different groups share the SMs)
+    batch.tune(contexts=1)
+    step_device()
+    torch.cuda.synchronize()
+    batch.profile(True)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    pe1.record(stream)
+    torch.cuda.synchronize()
+    ms_serial_step = pe0.elapsed_time(pe1) / args.steps
+    ktimes = batch.kernel_times()
+    batch.profile(False)
+    batch.tune(contexts=args.contexts or 3)
     ms_step = ms_total / args.steps
     audio_sec_per_step = world * S * args.secs
     value = audio_sec_per_step / (ms_step / 1e3)
@@ -274,6 +288,7 @@ def main():
                 "avg_launch_ms": dom_ms / max(dom_launches, 1),
                 "kernel_share_of_step": dom_ms / max(kernel_ms_sum, 1e-9),
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
+                "serialised_ms_per_step": ms_serial_step,
                 "compulsory_io_frac": (8.0 * n * S) / (ms_step / 1e3) / 1e9 / peak}
 
     # ---- end to end through the host-buffer entry point ----

@@ -117,8 +117,9 @@ int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);
 enum { PVGPU_KINDS = 8 };
 int pvgpu_batch_profile(pvgpu_batch *b, int enable);
 int pvgpu_batch_kernel_times(pvgpu_batch *b, double *ms /*[PVGPU_KINDS]*/, int64_t *count /*[PVGPU_KINDS]*/);
-/* tuning: frames per chunk and rows per group (0 = keep) */
-int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group);
+/* tuning (0 = keep): frames per chunk, rows per group, and how many groups are in flight at once (1..4; each has its
+ * own stream, workspace and staging buffers) */
+int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, int contexts);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage hooks for the parity tests (tests/ compares each stage with the CPU oracle).  Device work,
