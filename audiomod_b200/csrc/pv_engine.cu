@@ -92,12 +92,13 @@ struct Pipeline {
     Tables t;
     DevPlan p{};
     int device = 0;
-    DevBuf b_window, b_twf, b_twi, b_stwf, b_stwi, b_perm, b_omega, b_rstab;
+    DevBuf b_window, b_twf, b_twi, b_stwf, b_stwi, b_perm, b_omega, b_rstab, b_rsquad;
     // schedule on the device
     DevBuf b_recs, b_norm, b_whisper, b_carmag, b_carph;
     long recs_base = 0, recs_count = 0;
     int64_t norm_base = 0;
     int max_consumed = 1;   // largest per-slice contribution to the normalised stream seen so far
+    int max_out = 1;        // largest per-slice output count seen so far
     int ola_run = 16;       // slices per CTA of k_ola_resample
     int64_t launches = 0;
     // optional per-kernel timing with CUDA events on the launching stream
@@ -171,6 +172,19 @@ struct Pipeline {
         p.perm = b_perm.as<uint16_t>();
         p.omega = b_omega.as<float>();
         p.rs_table = b_rstab.as<float>();
+        if (p.rs_active && !d.rs.direct) {
+            const std::vector<float> &tab = d.rs.table;
+            const int n = (int)tab.size();
+            std::vector<float> quads((size_t)4 * n);
+            for (int e = 0; e < n; ++e) {
+                quads[4 * e + 0] = e >= 2 ? tab[e - 2] : 0.f;
+                quads[4 * e + 1] = e >= 1 ? tab[e - 1] : 0.f;
+                quads[4 * e + 2] = tab[e];
+                quads[4 * e + 3] = e + 1 < n ? tab[e + 1] : 0.f;
+            }
+            if ((rc = upload(b_rsquad, quads.data(), sizeof(float) * quads.size()))) return rc;
+        }
+        p.rs_quads = b_rsquad.as<float4>();
         return PVGPU_OK;
     }
 
@@ -193,7 +207,7 @@ struct Pipeline {
         recs_base = s.recs_base();
         recs_count = (long)recs.size();
         norm_base = s.norm_base();
-        for (const SliceRec &r : recs) max_consumed = std::max(max_consumed, std::max(r.consumed, r.shift_inc));
+        for (const SliceRec &r : recs) { max_consumed = std::max(max_consumed, std::max(r.consumed, r.shift_inc)); max_out = std::max(max_out, r.n_res); }
         return PVGPU_OK;
     }
 
@@ -224,7 +238,7 @@ struct Pipeline {
         launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st);
         span_end(sp, st); ++launches;
         sp = span_begin(3, st);
-        launch_ola_resample(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, ola_run, max_consumed, st);
+        launch_ola_resample(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, ola_run, max_consumed, max_out, st);
         span_end(sp, st); ++launches;
     }
 };

@@ -28,6 +28,7 @@ struct DevPlan {
     uint32_t rs_num, rs_den, rs_filt_len, rs_oversample;
     int rs_int_adv, rs_frac_adv;
     const float *rs_table;
+    const float4 *rs_quads;             // [rs_table_len] (tab[e-2], tab[e-1], tab[e], tab[e+1]) for the interpolated mode
     int rs_table_len;
 };
 
@@ -61,7 +62,7 @@ void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag,
 // overlap-add + normalisation (+ resampler when p.rs_active); `run` consecutive slices per CTA, max_consumed = the largest
 // number of normalised samples any slice contributes
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
-                         long k0, int nframes, int run, int max_consumed, cudaStream_t st);
+                         long k0, int nframes, int run, int max_consumed, int max_out, cudaStream_t st);
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
 
