@@ -99,7 +99,12 @@ struct Pipeline {
     int64_t norm_base = 0;
     int max_consumed = 1;   // largest per-slice contribution to the normalised stream seen so far
     int max_out = 1;        // largest per-slice output count seen so far
-    int ola_run = 16;       // slices per CTA of k_ola_resample
+    int ola_run = 16;       // slices per CTA of k_ola_resample (upper bound)
+    // host copy of the uploaded records + the resampler work lists built from them (ResampleRun, pv_kernels.cuh)
+    std::vector<SliceRec> h_recs;
+    DevBuf b_runs, b_rsent, b_rsfrac;
+    long run_origin = 0;
+    int table_run = 1;
     int64_t launches = 0;
     // optional per-kernel timing with CUDA events on the launching stream
     bool profile = false;
@@ -208,6 +213,70 @@ struct Pipeline {
         recs_count = (long)recs.size();
         norm_base = s.norm_base();
         for (const SliceRec &r : recs) { max_consumed = std::max(max_consumed, std::max(r.consumed, r.shift_inc)); max_out = std::max(max_out, r.n_res); }
+        h_recs = recs;
+        return PVGPU_OK;
+    }
+
+    // Work lists of k_ola_resample for slices [origin, end) in runs of `run` slices (launches must start at
+    // origin + multiple of run).  Output positions follow the reference's stepping (resample.c:548-554).
+    int build_resample_runs(long origin, long end, int run, cudaStream_t st) {
+        run_origin = origin;
+        table_run = run;
+        if (!p.rs_active) return PVGPU_OK;
+        const int L = (int)p.rs_filt_len, ov = (int)p.rs_oversample, nb = p.rs_direct ? 1 : ov;
+        if (L > kResPad) return fail(PVGPU_EINVAL, "resampler filter of %d taps is not supported (max %d)", L, kResPad);
+        std::vector<ResampleRun> runs;
+        std::vector<unsigned> ent;
+        std::vector<float> frac;
+        std::vector<unsigned> be[kMaxBuckets];
+        std::vector<float> bf[kMaxBuckets];
+        for (long ka = origin; ka < end; ka += run) {
+            const long kb = std::min<long>(ka + run, end);
+            const SliceRec &ra = h_recs[ka - recs_base];
+            ResampleRun hdr{};
+            hdr.u_lo = std::max<int64_t>(0, ra.res_off + ra.rs_last - L + 1);
+            hdr.out_first = ra.out_off;
+            hdr.ent_off = (int)ent.size();
+            for (int q = 0; q < nb; ++q) { be[q].clear(); bf[q].clear(); }
+            for (long k = ka; k < kb; ++k) {
+                const SliceRec &r = h_recs[k - recs_base];
+                if (r.flags & 1) continue;
+                int last = r.rs_last;
+                uint32_t fn = r.rs_frac;
+                for (int i = 0; i < r.n_write; ++i) {
+                    const int bucket = p.rs_direct ? 0 : (int)(fn * (uint32_t)ov / p.rs_den);
+                    const int64_t rel = r.res_off + last - L + 1 - hdr.u_lo + kResPad;
+                    const int64_t orel = r.out_off - hdr.out_first + i;
+                    if (rel < 0 || rel > 65535 || orel > 65534) return fail(PVGPU_ESTATE, "resampler run does not fit its packed work list");
+                    be[bucket].push_back(((unsigned)rel << 16) | (unsigned)orel);
+                    float fv;
+                    if (p.rs_direct) { std::memcpy(&fv, &fn, sizeof fv); }
+                    else fv = ((float)((fn * (uint32_t)ov) % p.rs_den)) / p.rs_den;
+                    bf[bucket].push_back(fv);
+                    last += p.rs_int_adv;
+                    fn += (uint32_t)p.rs_frac_adv;
+                    if (fn >= p.rs_den) { fn -= p.rs_den; ++last; }
+                }
+            }
+            int pos = 0;
+            for (int q = 0; q < nb; ++q) {
+                hdr.start[q] = pos;
+                ent.insert(ent.end(), be[q].begin(), be[q].end());
+                frac.insert(frac.end(), bf[q].begin(), bf[q].end());
+                pos += (int)be[q].size();
+                while (pos & 31) { ent.push_back(0xffffffffu); frac.push_back(0.f); ++pos; }
+            }
+            for (int q = nb; q <= kMaxBuckets; ++q) hdr.start[q] = pos;
+            hdr.padded = pos;
+            runs.push_back(hdr);
+        }
+        CU(b_runs.ensure(sizeof(ResampleRun) * std::max<size_t>(runs.size(), 1)));
+        CU(b_rsent.ensure(sizeof(unsigned) * std::max<size_t>(ent.size(), 1)));
+        CU(b_rsfrac.ensure(sizeof(float) * std::max<size_t>(frac.size(), 1)));
+        if (!runs.empty()) CU(cudaMemcpyAsync(b_runs.p, runs.data(), sizeof(ResampleRun) * runs.size(), cudaMemcpyHostToDevice, st));
+        if (!ent.empty()) CU(cudaMemcpyAsync(b_rsent.p, ent.data(), sizeof(unsigned) * ent.size(), cudaMemcpyHostToDevice, st));
+        if (!frac.empty()) CU(cudaMemcpyAsync(b_rsfrac.p, frac.data(), sizeof(float) * frac.size(), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));   // the host vectors are temporaries
         return PVGPU_OK;
     }
 
@@ -238,7 +307,8 @@ struct Pipeline {
         launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st);
         span_end(sp, st); ++launches;
         sp = span_begin(3, st);
-        launch_ola_resample(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, ola_run, max_consumed, max_out, st);
+        launch_ola_resample(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, table_run, max_consumed, b_runs.as<ResampleRun>(),
+                            b_rsent.as<unsigned>(), b_rsfrac.as<float>(), run_origin, st);
         span_end(sp, st); ++launches;
     }
 };
@@ -333,6 +403,16 @@ struct pvgpu_batch {
         for (auto &c : ctx) { if (c.st) cudaStreamDestroy(c.st); if (c.done) cudaEventDestroy(c.done); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (stream) cudaStreamDestroy(stream);
+    }
+    int run_for_chunk = 0;   // frames_per_chunk the resampler work lists were built for
+    int prepare_runs() {
+        if (run_for_chunk == frames_per_chunk) return PVGPU_OK;
+        int run = ola_run_limit(pl.p, pl.ola_run, pl.max_consumed, pl.max_out);
+        while (run > 1 && frames_per_chunk % run) --run;   // chunks must start on run boundaries
+        int rc = pl.build_resample_runs(0, n_slices, run, stream);
+        if (rc) return rc;
+        run_for_chunk = frames_per_chunk;
+        return PVGPU_OK;
     }
     int group_rows() const {
         const int C = cfg.channels, total = n_streams * C;
@@ -475,6 +555,8 @@ int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_
         CU(cudaDeviceSynchronize());
     }
     CU(cudaDeviceSynchronize());
+    b->run_for_chunk = 0;
+    if ((rc = b->prepare_runs())) return rc;
     b->planned = true;
     return PVGPU_OK;
 }
@@ -515,6 +597,7 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
     int rc;
     for (int i = 0; i < n_ctx; ++i)
         if ((rc = b->ctx[i].ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
+    if ((rc = b->prepare_runs())) return rc;
     b->pl.launches = 0;
     // fork: the contexts start after everything already queued on the caller's stream
     CU(cudaEventRecord(b->ev_fork, st));
@@ -582,6 +665,7 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
         CU(c.stage_in.ensure(sizeof(float) * (size_t)group * in_stride));
         CU(c.stage_out.ensure(sizeof(float) * (size_t)group * out_stride));
     }
+    if ((rc = b->prepare_runs())) return rc;
     b->pl.launches = 0;
     b->h2d = b->d2h = 0;
     // each context's stream carries H2D -> kernels -> D2H of its groups in order; the contexts run concurrently, so the
@@ -761,6 +845,7 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     CU(cudaMemcpyAsync(s->d_len.p, lim.data(), sizeof(int64_t) * lim.size(), cudaMemcpyHostToDevice, s->st));
     int rc;
     if ((rc = pl.upload_schedule(sc, s->st))) return rc;
+    if ((rc = pl.build_resample_runs(k0, k0 + added, ola_run_limit(p, 8, pl.max_consumed, pl.max_out), s->st))) return rc;
     const SliceRec &first = sc.recs()[k0 - sc.recs_base()];
     const int64_t out_base = first.out_off;
     const int64_t new_out = sc.total_out() - out_base;

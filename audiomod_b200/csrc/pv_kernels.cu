@@ -561,8 +561,7 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
 // ------------------------------------------------------------------------------------------------
 constexpr int kOlaMaxSlices = 48;   // run + history slices held in the CTA's tables
 constexpr int kOlaMaxFrames = 96;   // frames overlapping them
-constexpr int kMaxBuckets = 8;      // resampler table phases (oversample <= 8 at quality 4)
-constexpr int kResPad = 512;        // bias that keeps the packed tap-0 offset non-negative at the start of a stream
+
 
 struct OlaTables {
     int64_t res_off[kOlaMaxSlices + 1];   // resampler-stream offset of each table slice (+ end sentinel)
@@ -571,14 +570,14 @@ struct OlaTables {
     int fr_off[kOlaMaxFrames];            // ola_off of frame (jmin + i) relative to ola_base
     int fr_slot[kOlaMaxFrames];           // its slot in the frame ring
     int out_pref[kOlaMaxSlices + 1];      // flattened output index of each run slice
-    int bucket[2 * kMaxBuckets + 1];      // counts | starts | padded total
     long kmin, jmin;
     int nsl, nfr;
     int64_t ola_base, u_lo, u_hi;
 };
 
 __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
-                                                      int64_t norm_base, long recs_base, long k0, int nf, int run, int max_in, int out_cap) {
+                                                      int64_t norm_base, long recs_base, long k0, int nf, int run, int max_in, const ResampleRun *__restrict__ runs,
+                                                      const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, long run_origin) {
     extern __shared__ float4 smem4[];
     __shared__ OlaTables T;
     const int row = blockIdx.y;
@@ -669,65 +668,33 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
     __syncthreads();
 
     // ---- resampler ----
-    // Outputs of the run are bucketed by their table phase (`offset` in resample.c:470): every output of a bucket
-    // reads the same sinc-table quad at every tap, so a warp that works on one bucket gets the quad with a single
-    // broadcast shared-memory access instead of 32 different 16-byte reads.  Buckets start at multiples of 32.
-    const int total_out = T.out_pref[kb - ka];
-    const int nrun = (int)(kb - ka);
+    // The host has bucketed the outputs of this run by their table phase (`offset` in resample.c:470), in output order
+    // inside a bucket and with buckets starting at multiples of 32 (ResampleRun, pv_kernels.cuh).  A warp therefore
+    // works on one phase: the sinc quad of every tap is a single broadcast shared-memory access, and the lanes' input
+    // windows are a constant few samples apart (bank-conflict free).
+    const ResampleRun hdr = runs[(ka - run_origin) / run];
     const int ov = (int)p.rs_oversample;
     const int nb = p.rs_direct ? 1 : ov;
-    float *s_frac = s_in + max_in;                    // [cap] interpolation fraction of each bucketed output
-    unsigned *s_ent = (unsigned *)(s_frac + out_cap); // [cap] (tap-0 position in s_in) << 16 | (output index relative to the run)
-    if (tid < 2 * kMaxBuckets + 1) T.bucket[tid] = 0;
-    for (int e = tid; e < out_cap; e += blockDim.x) s_ent[e] = 0xffffffffu;
-    __syncthreads();
-    const int64_t out_first = recs[ka - recs_base].out_off;
-    // pass 1: count; pass 2: place
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int e = tid; e < total_out; e += blockDim.x) {
-            int ks = 0;
-            while (ks + 1 < nrun && T.out_pref[ks + 1] <= e) ++ks;
-            const int i = e - T.out_pref[ks];
-            const SliceRec &r = recs[ka + ks - recs_base];
-            // position of output i: i steps of (int_advance, frac_advance) with carry (resample.c:548-554)
-            const uint64_t fq = (uint64_t)r.rs_frac + (uint64_t)i * (uint64_t)p.rs_frac_adv;
-            const int last = r.rs_last + i * p.rs_int_adv + (int)(fq / p.rs_den);
-            const uint32_t frac_num = (uint32_t)(fq % p.rs_den);
-            const int bucket = p.rs_direct ? 0 : (int)(frac_num * (uint32_t)ov / p.rs_den);
-            if (pass == 0) {
-                atomicAdd(&T.bucket[bucket], 1);
-            } else {
-                const int slot = T.bucket[kMaxBuckets + bucket] + atomicAdd(&T.bucket[bucket], 1);
-                const int64_t pos0 = r.res_off + last - L + 1;   // resampler-stream position of tap 0 (negative: zero history)
-                s_frac[slot] = p.rs_direct ? __uint_as_float(frac_num) : ((float)((frac_num * (uint32_t)ov) % p.rs_den)) / p.rs_den;
-                s_ent[slot] = ((unsigned)(pos0 - u_lo + kResPad) << 16) | (unsigned)(r.out_off - out_first + i);
-            }
-        }
-        __syncthreads();
-        if (pass == 0 && tid == 0) {
-            int start = 0;
-            for (int q = 0; q < nb; ++q) { T.bucket[kMaxBuckets + q] = start; start += (T.bucket[q] + 31) & ~31; T.bucket[q] = 0; }
-            T.bucket[2 * kMaxBuckets] = start;
-        }
-        __syncthreads();
-    }
-    const int padded = T.bucket[2 * kMaxBuckets];
-    float *__restrict__ orow = g.out + row_out + out_first;
-    for (int e = tid; e < padded; e += blockDim.x) {
-        const unsigned ent = s_ent[e];
+    const unsigned *__restrict__ ent_tab = rs_ent + hdr.ent_off;
+    const float *__restrict__ frac_tab = rs_frac + hdr.ent_off;
+    float *__restrict__ orow = g.out + row_out + hdr.out_first;
+    const int64_t out_limit = g.n_out[row] - hdr.out_first;
+    const int in_shift = (int)(hdr.u_lo - u_lo);   // 0: the header's span start is the one used above
+    for (int e = tid; e < hdr.padded; e += blockDim.x) {
+        const unsigned ent = __ldg(&ent_tab[e]);
         int bucket = 0;
-        while (bucket + 1 < nb && T.bucket[kMaxBuckets + bucket + 1] <= (e & ~31)) ++bucket;   // warp-uniform
-        if (ent == 0xffffffffu) continue;
-        const int rel = (int)(ent >> 16) - kResPad;   // tap-0 offset into s_in; negative only at the very start of a stream
+        while (bucket + 1 < nb && hdr.start[bucket + 1] <= (e & ~31)) ++bucket;   // warp-uniform
+        if (ent == 0xffffffffu || (int64_t)(ent & 0xffffu) >= out_limit) continue;
+        const int rel = (int)(ent >> 16) - kResPad + in_shift;   // tap-0 offset into s_in; negative only at the very start of a stream
         const int jbeg = rel < 0 ? min(L, -rel) : 0;
         const float *xs = s_in + rel;
         float sum;
         if (p.rs_direct) {
             sum = 0.f;
-            const float *__restrict__ tt = p.rs_table + (size_t)__float_as_uint(s_frac[e]) * L;
+            const float *__restrict__ tt = p.rs_table + (size_t)__float_as_uint(__ldg(&frac_tab[e])) * L;
             for (int j = jbeg; j < L; ++j) sum += xs[j] * __ldg(&tt[j]);
         } else {
-            const float frac = s_frac[e];
+            const float frac = __ldg(&frac_tab[e]);
             const float4 *q = s_quad + 4 + ov - bucket;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
@@ -838,19 +805,24 @@ void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag,
     k_synthesise<<<grid, fft_threads(p), smem_synthesise(p), st>>>(p, g, car_mag, car_phase, k0);
 }
 
-void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
-                         long k0, int nframes, int run, int max_consumed, int max_out, cudaStream_t st) {
+int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out) {
     if (run > kOlaMaxSlices - 16) run = kOlaMaxSlices - 16;
     if (run < 1) run = 1;
     const int L = p.rs_active ? (int)p.rs_filt_len : 1;
-    const bool quad = p.rs_active && !p.rs_direct;
     // the packed per-output entry holds two 16-bit fields: keep the span and the output count of a run below 64k - pad
-    while (run > 1 && (run * max_consumed + L + 8 + kResPad >= 65536 || run * max_out >= 65536)) run /= 2;
+    while (run > 1 && (run * max_consumed + L + 8 + kResPad >= 65536 || run * max_out >= 65535)) run /= 2;
+    return run;
+}
+
+void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
+                         long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
+                         long run_origin, cudaStream_t st) {
+    const int L = p.rs_active ? (int)p.rs_filt_len : 1;
+    const bool quad = p.rs_active && !p.rs_direct;
     const int max_in = ((run * max_consumed + L + 8) + 3) & ~3;
-    const int out_cap = p.rs_active ? run * max_out + 32 * kMaxBuckets : 0;
-    const size_t sm = (quad ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)max_in + 2 * sizeof(float) * (size_t)out_cap;
+    const size_t sm = (quad ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)max_in;
     dim3 grid((nframes + run - 1) / run, g.rows);
-    k_ola_resample<<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, out_cap);
+    k_ola_resample<<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, run_origin);
 }
 
 }  // namespace pvgpu

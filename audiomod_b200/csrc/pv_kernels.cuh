@@ -59,10 +59,29 @@ void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table /
                         long k0, int nframes, cudaStream_t st);
 void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase /*[slices][Hp] indexed by absolute slice, or null*/,
                        long k0, int nframes, cudaStream_t st);
-// overlap-add + normalisation (+ resampler when p.rs_active); `run` consecutive slices per CTA, max_consumed = the largest
-// number of normalised samples any slice contributes
+// Host-built work list of the resampler for one run of slices (see k_ola_resample): the run's outputs bucketed by
+// sinc-table phase, output order inside a bucket, buckets padded to multiples of 32.  Entry = (tap-0 position relative to
+// u_lo + kResPad) << 16 | (output position relative to out_first); 0xffffffff = padding.  rs_frac holds the cubic
+// interpolation fraction of each entry (interpolated mode) or the table phase as raw bits (direct mode).
+constexpr int kMaxBuckets = 8;      // resampler table phases (oversample <= 8 at quality 4)
+constexpr int kResPad = 1024;       // bias that keeps the packed tap-0 offset non-negative at the start of a stream
+struct ResampleRun {
+    int64_t u_lo;        // first normalised-stream position the run reads (clipped to 0)
+    int64_t out_first;   // output position of the run's first slice
+    int ent_off;         // offset of the run's entries in rs_ent / rs_frac
+    int padded;          // entries including padding
+    int start[kMaxBuckets + 1];
+    int pad[3];
+};
+static_assert(sizeof(ResampleRun) == 72, "ResampleRun layout");
+
+// largest run (slices per CTA) not above `run` that the packed entries and the CTA tables can hold
+int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out);
+// overlap-add + normalisation (+ resampler when p.rs_active); `run` consecutive slices per CTA starting at k0 (which must
+// be run_origin + a multiple of run), max_consumed = the largest number of normalised samples any slice contributes
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
-                         long k0, int nframes, int run, int max_consumed, int max_out, cudaStream_t st);
+                         long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
+                         long run_origin, cudaStream_t st);
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
 
