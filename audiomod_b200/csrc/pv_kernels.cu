@@ -575,6 +575,7 @@ struct OlaTables {
     int64_t ola_base, u_lo, u_hi;
 };
 
+template <int OV>   // sinc-table oversampling of the interpolated resampler mode; 0 = direct table or no resampler
 __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
                                                       int64_t norm_base, long recs_base, long k0, int nf, int run, int max_in, const ResampleRun *__restrict__ runs,
                                                       const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, long run_origin) {
@@ -586,8 +587,10 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
     const int L = p.rs_active ? (int)p.rs_filt_len : 1;
     const bool quad = p.rs_active && !p.rs_direct;
     float4 *s_quad = smem4;
-    float *s_in = (float *)(smem4 + (quad ? p.rs_table_len : 0));
+    // s_in[-L .. 0) stays zero: the resampler's history before the start of a stream (speex mem is zero-initialised)
+    float *s_in = (float *)(smem4 + (quad ? p.rs_table_len : 0)) + (p.rs_active ? L : 0);
     const int tid = threadIdx.x;
+    if (p.rs_active) for (int i = tid; i < L; i += blockDim.x) s_in[i - L] = 0.f;
 
     if (tid == 0) {
         // slices whose normalised samples are needed: the run plus the resampler history before it
@@ -673,38 +676,38 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
     // works on one phase: the sinc quad of every tap is a single broadcast shared-memory access, and the lanes' input
     // windows are a constant few samples apart (bank-conflict free).
     const ResampleRun hdr = runs[(ka - run_origin) / run];
-    const int ov = (int)p.rs_oversample;
-    const int nb = p.rs_direct ? 1 : ov;
+    constexpr int nb = OV > 0 ? OV : 1;
     const unsigned *__restrict__ ent_tab = rs_ent + hdr.ent_off;
     const float *__restrict__ frac_tab = rs_frac + hdr.ent_off;
     float *__restrict__ orow = g.out + row_out + hdr.out_first;
     const int64_t out_limit = g.n_out[row] - hdr.out_first;
-    const int in_shift = (int)(hdr.u_lo - u_lo);   // 0: the header's span start is the one used above
+    const int in_shift = (int)(hdr.u_lo - u_lo) - kResPad;   // hdr.u_lo == u_lo; entries are biased by kResPad
     for (int e = tid; e < hdr.padded; e += blockDim.x) {
         const unsigned ent = __ldg(&ent_tab[e]);
         int bucket = 0;
-        while (bucket + 1 < nb && hdr.start[bucket + 1] <= (e & ~31)) ++bucket;   // warp-uniform
+#pragma unroll
+        for (int q = 1; q < nb; ++q) bucket += hdr.start[q] <= (e & ~31);   // warp-uniform
         if (ent == 0xffffffffu || (int64_t)(ent & 0xffffu) >= out_limit) continue;
-        const int rel = (int)(ent >> 16) - kResPad + in_shift;   // tap-0 offset into s_in; negative only at the very start of a stream
-        const int jbeg = rel < 0 ? min(L, -rel) : 0;
-        const float *xs = s_in + rel;
+        const float *xs = s_in + ((int)(ent >> 16) + in_shift);   // tap 0; may reach into the zero history before s_in[0]
         float sum;
-        if (p.rs_direct) {
+        if (OV == 0) {
             sum = 0.f;
             const float *__restrict__ tt = p.rs_table + (size_t)__float_as_uint(__ldg(&frac_tab[e])) * L;
-            for (int j = jbeg; j < L; ++j) sum += xs[j] * __ldg(&tt[j]);
+            for (int j = 0; j < L; ++j) sum += xs[j] * __ldg(&tt[j]);
         } else {
             const float frac = __ldg(&frac_tab[e]);
-            const float4 *q = s_quad + 4 + ov - bucket;
+            const float4 *q = s_quad + 4 + OV - bucket;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-            for (int j = jbeg; j < L; ++j) {
-                const float v = xs[j];
-                const float4 tq = q[j * ov];
-                a0 += v * tq.x;
-                a1 += v * tq.y;
-                a2 += v * tq.z;
-                a3 += v * tq.w;
+            for (int j = 0; j < L; j += 4) {   // filt_len is a multiple of 4 (resample.c:712)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float v = xs[j + u];
+                    const float4 tq = q[(j + u) * OV];
+                    a0 += v * tq.x;
+                    a1 += v * tq.y;
+                    a2 += v * tq.z;
+                    a3 += v * tq.w;
+                }
             }
             // cubic_coef (resample.c:339-351)
             const float i0 = -0.16667f * frac + 0.16667f * frac * frac * frac;
@@ -738,7 +741,11 @@ cudaError_t configure_kernels() {
     const int big = 200 * 1024;
     if ((e = cudaFuncSetAttribute(k_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_synthesise, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -820,9 +827,15 @@ void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *rec
     const int L = p.rs_active ? (int)p.rs_filt_len : 1;
     const bool quad = p.rs_active && !p.rs_direct;
     const int max_in = ((run * max_consumed + L + 8) + 3) & ~3;
-    const size_t sm = (quad ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)max_in;
+    const size_t sm = (quad ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)(max_in + (p.rs_active ? L : 0));
     dim3 grid((nframes + run - 1) / run, g.rows);
-    k_ola_resample<<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, run_origin);
+#define PV_OLA(OVV) k_ola_resample<OVV><<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, run_origin)
+    if (!quad) PV_OLA(0);
+    else if (p.rs_oversample == 8) PV_OLA(8);
+    else if (p.rs_oversample == 4) PV_OLA(4);
+    else if (p.rs_oversample == 2) PV_OLA(2);
+    else PV_OLA(1);
+#undef PV_OLA
 }
 
 }  // namespace pvgpu
