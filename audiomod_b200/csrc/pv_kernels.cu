@@ -191,6 +191,18 @@ __device__ __forceinline__ double princarg_rn(double a) {
     return __dadd_rn(__dsub_rn(x, __dmul_rn(m2pi, q)), pi);
 }
 
+// Same value, cheaper: floor(x / -2pi) is taken from x * fl(-1/2pi) whenever that product is safely away from an
+// integer (the two differ by < 4e-16 |q|); otherwise the exact division decides.
+__device__ __forceinline__ double princarg_fast(double a) {
+    const double pi = 3.14159265358979323846, m2pi = -2.0 * 3.14159265358979323846;
+    const double x = __dadd_rn(a, pi);
+    const double qa = __dmul_rn(x, -0.15915494309189535);
+    double n = floor(qa);
+    const double fr = qa - n;
+    if (!(fr > 1e-9 && fr < 1.0 - 1e-9 && fabs(qa) < 1e6)) n = floor(__ddiv_rn(x, m2pi));
+    return __dadd_rn(__dsub_rn(x, __dmul_rn(m2pi, n)), pi);
+}
+
 __device__ __forceinline__ float sub3_rn(float a, float b, float c) { return __fsub_rn(__fsub_rn(a, b), c); }
 
 // One CTA per stream; frames and channels are visited in the reference's order because the peak
@@ -343,6 +355,191 @@ __global__ void k_phase_core(const DevPlan p, const DevRows g, const SliceRec *_
     const int nprev = s_misc[1];
     for (int i = tid; i < nprev; i += nthr) gpk[1 + i] = s_prev[i];
     if (tid == 0) { gpk[0] = nprev; g.started[stream] = s_misc[2] ? 0 : 1; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_phase_lock_t<E>: the phase-locked core (coremode 1) for the templated FFT sizes.  One CTA per stream, half/E
+// threads, thread t owns the E contiguous bins [E*t, E*t+E).  Same arithmetic as k_phase_core<true>; differences are
+// purely organisational:
+//  * the next (frame, channel)'s magnitudes and phases are prefetched into registers with 128-bit loads while the
+//    current one is processed (the kernel is serial in time, so global latency would otherwise be exposed every frame);
+//  * a thread handles its own peaks (at most ceil(E/3): peaks are >= 3 bins apart), so the analysis phase of a peak is
+//    already in its registers, and the region of a bin is one of the two peaks around the thread's first bin -- no search;
+//  * current / previous peak lists ping-pong instead of being copied; four block barriers per (frame, channel).
+// ------------------------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base, long k0,
+                                                      int nframes) {
+    static_assert(E == 4 || E == 8, "bins per thread");
+    constexpr int kMaxOwn = (E + 2) / 3;
+    extern __shared__ float smem[];
+    const int half = p.half, C = g.channels, maxpk = g.maxpk;
+    float *s_mag = smem;                          // half + 8 (two guard bins each side are never peaks, but are read)
+    float *s_pp = s_mag + half + 8;               // C * half   previous analysis phase
+    float *s_po = s_pp + C * half;                // C * half   previous output phase
+    int *s_pk0 = (int *)(s_po + C * half);        // maxpk      peak list A
+    int *s_pk1 = s_pk0 + maxpk;                   // maxpk      peak list B
+    int *s_start = s_pk1 + maxpk;                 // maxpk + 1
+    float *s_rot = (float *)(s_start + maxpk + 1);  // maxpk
+    int *s_wsum = (int *)(s_rot + maxpk);         // 32
+    const int stream = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int b0 = tid * E;
+
+    for (int c = 0; c < C; ++c) {
+        const int64_t row = (int64_t)stream * C + c;
+        for (int i = tid; i < half; i += nthr) {
+            s_pp[c * half + i] = g.prev_phase[row * half + i];
+            s_po[c * half + i] = g.prev_out[row * half + i];
+        }
+    }
+    int *gpk = g.peaks + (int64_t)stream * (1 + maxpk);
+    int nprev = gpk[0];
+    bool first = g.started[stream] == 0;
+    int *s_prev = s_pk0, *s_cur = s_pk1;
+    for (int i = tid; i < nprev; i += nthr) s_prev[i] = gpk[1 + i];
+    if (tid < 4) { s_mag[half + 4 + tid] = 0.f; }
+
+    const int total = nframes * C;
+    float mg[E], phv[E];
+    auto fetch = [&](int it) {
+        const int f = it / C, c = it - f * C;
+        const int64_t base = (((int64_t)stream * C + c) * g.F + f) * p.Hp + b0;
+#pragma unroll
+        for (int e = 0; e < E; e += 4) {
+            const float4 m4 = *(const float4 *)(g.mag + base + e);
+            const float4 p4 = *(const float4 *)(g.phase + base + e);
+            mg[e] = m4.x; mg[e + 1] = m4.y; mg[e + 2] = m4.z; mg[e + 3] = m4.w;
+            phv[e] = p4.x; phv[e + 1] = p4.y; phv[e + 2] = p4.z; phv[e + 3] = p4.w;
+        }
+    };
+    if (total > 0) fetch(0);
+    const float hopf = (float)p.hop;
+    __syncthreads();
+
+    for (int it = 0; it < total; ++it) {
+        const int f = it / C, c = it - f * C;
+        const float phase_inc = (float)recs[k0 + f - recs_base].phase_inc;
+        float *pp = s_pp + c * half, *po = s_po + c * half;
+        float ph[E], m[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { ph[e] = phv[e]; m[e] = mg[e]; }
+#pragma unroll
+        for (int e = 0; e < E; e += 4) *(float4 *)(s_mag + 4 + b0 + e) = make_float4(m[e], m[e + 1], m[e + 2], m[e + 3]);
+        __syncthreads();   // (A) magnitudes visible
+        // peak picking (:587-596): strict +-2 local maxima with 2 <= b <= half-3
+        float w[E + 4];
+        w[0] = s_mag[4 + b0 - 2]; w[1] = s_mag[4 + b0 - 1];
+#pragma unroll
+        for (int e = 0; e < E; ++e) w[2 + e] = m[e];
+        w[E + 2] = s_mag[4 + b0 + E]; w[E + 3] = s_mag[4 + b0 + E + 1];
+        unsigned flags = 0;
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int b = b0 + e;
+            const bool pk = b >= 2 && b + 2 < half && w[e + 2] > w[e + 1] && w[e + 2] > w[e] && w[e + 2] > w[e + 3] && w[e + 2] > w[e + 4];
+            flags |= (unsigned)pk << e;
+            cnt += pk;
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        if (it + 1 < total) fetch(it + 1);   // prefetch the next (frame, channel) while this one is processed
+        __syncthreads();   // (B)
+        int base = 0, npk = 0;
+        for (int wv = 0; wv < nwarp; ++wv) { const int v = s_wsum[wv]; npk += v; if (wv < warp) base += v; }
+        base += incl - cnt;   // peaks before this thread's first bin
+        {
+            int r = base;
+#pragma unroll
+            for (int e = 0; e < E; ++e) if (flags & (1u << e)) s_cur[r++] = b0 + e;
+        }
+        float *__restrict__ gph = g.phase + (((int64_t)stream * C + c) * g.F + f) * p.Hp + b0;
+        if (first) {
+            // first call of the process: pass the analysis phase through and seed the state (:606-616)
+#pragma unroll
+            for (int e = 0; e < E; ++e) { pp[b0 + e] = ph[e]; po[b0 + e] = ph[e]; }
+            __syncthreads();   // (C) peak list complete
+        } else if (npk == 0 || nprev == 0) {
+            // classic propagation (:617-636)
+            float outv[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = b0 + e;
+                const float omega = __ldg(&p.omega[i]);
+                const float dphi = (float)__dadd_rn((double)omega, princarg_fast((double)sub3_rn(ph[e], pp[i], omega)));
+                const float adv = __fdiv_rn(__fmul_rn(dphi, phase_inc), hopf);
+                outv[e] = (float)princarg_fast((double)__fadd_rn(po[i], adv));
+                pp[i] = ph[e];
+                po[i] = outv[e];
+            }
+#pragma unroll
+            for (int e = 0; e < E; e += 4) *(float4 *)(gph + e) = make_float4(outv[e], outv[e + 1], outv[e + 2], outv[e + 3]);
+            __syncthreads();   // (C)
+        } else {
+            __syncthreads();   // (C) peak list complete
+            // own peaks: rotation (:641-667) and region start (:668-683)
+            {
+                int r = base;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if (!(flags & (1u << e))) continue;
+                    const int p2 = b0 + e;
+                    int lo = 0, hi = nprev;  // first previous peak >= p2
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prev[mid] < p2) lo = mid + 1; else hi = mid; }
+                    int j;
+                    if (lo == 0) j = 0;
+                    else if (lo == nprev) j = nprev - 1;
+                    else j = (s_prev[lo] - p2 < p2 - s_prev[lo - 1]) ? lo : lo - 1;  // ties keep the lower index (:644-652)
+                    const int p1 = s_prev[j];
+                    const float avg_p = (float)((double)(p1 + p2) * 0.5);
+                    const float pomega = (float)__ddiv_rn(__dmul_rn(p.two_pi_hop, (double)__fsub_rn(avg_p, 1.0f)), (double)p.N);
+                    const float dphi = (float)__dadd_rn((double)pomega, princarg_fast((double)sub3_rn(ph[e], pp[p1], pomega)));
+                    const float target = (float)princarg_fast((double)__fadd_rn(po[p1], __fdiv_rn(__fmul_rn(dphi, phase_inc), hopf)));
+                    s_rot[r] = (float)princarg_fast((double)__fsub_rn(target, ph[e]));
+                    s_start[r] = r == 0 ? 0 : (s_cur[r - 1] + p2 + 1) >> 1;  // round((a+b)*0.5), half away from zero
+                    ++r;
+                }
+                if (tid == 0) s_start[npk] = half;
+            }
+            __syncthreads();   // (D) rotations and region starts complete; all reads of the old state are done
+            // lock every bin to its region's peak (:685-699); the region of bin b0 is that of the peak before b0 or of the
+            // first peak at/after b0, and at most kMaxOwn more regions start inside the thread's bins
+            int pk = base < npk ? base : npk - 1;
+            if (pk > 0 && s_start[pk] > b0) --pk;
+            float outv[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int i = b0 + e;
+                while (s_start[pk + 1] <= i) ++pk;
+                outv[e] = (float)princarg_fast((double)__fadd_rn(ph[e], s_rot[pk]));
+                pp[i] = ph[e];
+                po[i] = outv[e];
+            }
+#pragma unroll
+            for (int e = 0; e < E; e += 4) *(float4 *)(gph + e) = make_float4(outv[e], outv[e + 1], outv[e + 2], outv[e + 3]);
+        }
+        // the list just built becomes the previous one (shared by the channels of the stream)
+        { int *tsw = s_prev; s_prev = s_cur; s_cur = tsw; }
+        nprev = npk;
+        first = false;
+        (void)kMaxOwn;
+    }
+    __syncthreads();
+    for (int c = 0; c < C; ++c) {
+        const int64_t row = (int64_t)stream * C + c;
+        for (int i = tid; i < half; i += nthr) {
+            g.prev_phase[row * half + i] = s_pp[c * half + i];
+            g.prev_out[row * half + i] = s_po[c * half + i];
+        }
+    }
+    for (int i = tid; i < nprev; i += nthr) gpk[1 + i] = s_prev[i];
+    if (tid == 0) { gpk[0] = nprev; g.started[stream] = (total > 0 || !first) ? 1 : 0; }
 }
 
 // coremode 2: phase *= phaseIncrement / hop (two float roundings, :558-572)
@@ -746,6 +943,8 @@ cudaError_t configure_kernels() {
     if ((e = cudaFuncSetAttribute(k_ola_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_ola_resample<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_ola_resample<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_phase_lock_t<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_phase_lock_t<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -778,6 +977,13 @@ void launch_phase_core(const DevPlan &p, const DevRows &g, int coremode, const S
         return;
     }
     const int streams = g.rows / g.channels;
+    if (coremode == 1 && (p.N == 512 || p.N == 1024 || p.N == 2048 || p.N == 4096 || p.N == 8192)) {
+        const int E = p.N == 8192 ? 8 : 4;
+        const size_t sm = sizeof(float) * ((size_t)p.half + 8 + (size_t)2 * g.channels * p.half + (size_t)4 * g.maxpk + 1 + 32 + 8);
+        if (E == 4) k_phase_lock_t<4><<<streams, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+        else k_phase_lock_t<8><<<streams, p.half / 8, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+        return;
+    }
     const size_t sm = smem_phase_core(p, g.channels, g.maxpk);
     int threads = p.half / 4;
     if (threads < 64) threads = 64;
@@ -848,7 +1054,7 @@ __global__ void k_test_atan2f(int64_t n, const float *__restrict__ y, const floa
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = pv_atan2f(y[i], x[i]);
 }
 __global__ void k_test_princarg(int64_t n, const double *__restrict__ a, double *__restrict__ out) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = princarg_rn(a[i]);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (i & 1) ? princarg_rn(a[i]) : princarg_fast(a[i]);
 }
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st) { k_test_atan2f<<<592, 256, 0, st>>>(n, y, x, out); }
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st) { k_test_princarg<<<592, 256, 0, st>>>(n, a, out); }
