@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const Dev
     extern __shared__ float smem[];
     const int half = p.half, C = g.channels, maxpk = g.maxpk;
     float *s_mag = smem;                          // half + 8 (two guard bins each side are never peaks, but are read)
-    float *s_pp = s_mag + half + 8;               // C * half   previous analysis phase
+    float *s_ph = s_mag + half + 8;               // half       analysis phase of the current frame (peaks read each other's)
+    float *s_pp = s_ph + half;                    // C * half   previous analysis phase
     float *s_po = s_pp + C * half;                // C * half   previous output phase
     int *s_pk0 = (int *)(s_po + C * half);        // maxpk      peak list A
     int *s_pk1 = s_pk0 + maxpk;                   // maxpk      peak list B
@@ -425,8 +426,11 @@ __global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const Dev
 #pragma unroll
         for (int e = 0; e < E; ++e) { ph[e] = phv[e]; m[e] = mg[e]; }
 #pragma unroll
-        for (int e = 0; e < E; e += 4) *(float4 *)(s_mag + 4 + b0 + e) = make_float4(m[e], m[e + 1], m[e + 2], m[e + 3]);
-        __syncthreads();   // (A) magnitudes visible
+        for (int e = 0; e < E; e += 4) {
+            *(float4 *)(s_mag + 4 + b0 + e) = make_float4(m[e], m[e + 1], m[e + 2], m[e + 3]);
+            *(float4 *)(s_ph + b0 + e) = make_float4(ph[e], ph[e + 1], ph[e + 2], ph[e + 3]);
+        }
+        __syncthreads();   // (A) magnitudes and phases visible
         // peak picking (:587-596): strict +-2 local maxima with 2 <= b <= half-3
         float w[E + 4];
         w[0] = s_mag[4 + b0 - 2]; w[1] = s_mag[4 + b0 - 1];
@@ -483,30 +487,26 @@ __global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const Dev
             __syncthreads();   // (C)
         } else {
             __syncthreads();   // (C) peak list complete
-            // own peaks: rotation (:641-667) and region start (:668-683)
-            {
-                int r = base;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    if (!(flags & (1u << e))) continue;
-                    const int p2 = b0 + e;
-                    int lo = 0, hi = nprev;  // first previous peak >= p2
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prev[mid] < p2) lo = mid + 1; else hi = mid; }
-                    int j;
-                    if (lo == 0) j = 0;
-                    else if (lo == nprev) j = nprev - 1;
-                    else j = (s_prev[lo] - p2 < p2 - s_prev[lo - 1]) ? lo : lo - 1;  // ties keep the lower index (:644-652)
-                    const int p1 = s_prev[j];
-                    const float avg_p = (float)((double)(p1 + p2) * 0.5);
-                    const float pomega = (float)__ddiv_rn(__dmul_rn(p.two_pi_hop, (double)__fsub_rn(avg_p, 1.0f)), (double)p.N);
-                    const float dphi = (float)__dadd_rn((double)pomega, princarg_fast((double)sub3_rn(ph[e], pp[p1], pomega)));
-                    const float target = (float)princarg_fast((double)__fadd_rn(po[p1], __fdiv_rn(__fmul_rn(dphi, phase_inc), hopf)));
-                    s_rot[r] = (float)princarg_fast((double)__fsub_rn(target, ph[e]));
-                    s_start[r] = r == 0 ? 0 : (s_cur[r - 1] + p2 + 1) >> 1;  // round((a+b)*0.5), half away from zero
-                    ++r;
-                }
-                if (tid == 0) s_start[npk] = half;
+            // one thread per peak of the compacted list: rotation (:641-667) and region start (:668-683)
+            for (int r = tid; r < npk; r += nthr) {
+                const int p2 = s_cur[r];
+                int lo = 0, hi = nprev;  // first previous peak >= p2
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prev[mid] < p2) lo = mid + 1; else hi = mid; }
+                int j;
+                if (lo == 0) j = 0;
+                else if (lo == nprev) j = nprev - 1;
+                else j = (s_prev[lo] - p2 < p2 - s_prev[lo - 1]) ? lo : lo - 1;  // ties keep the lower index (:644-652)
+                const int p1 = s_prev[j];
+                const float php = s_ph[p2];
+                const float avg_p = (float)((double)(p1 + p2) * 0.5);
+                // (2*pi*hop*(avg_p-1)) / N: N is a power of two, so the division is an exact scaling
+                const float pomega = (float)__dmul_rn(__dmul_rn(p.two_pi_hop, (double)__fsub_rn(avg_p, 1.0f)), (double)p.inv_n);
+                const float dphi = (float)__dadd_rn((double)pomega, princarg_fast((double)sub3_rn(php, pp[p1], pomega)));
+                const float target = (float)princarg_fast((double)__fadd_rn(po[p1], __fdiv_rn(__fmul_rn(dphi, phase_inc), hopf)));
+                s_rot[r] = (float)princarg_fast((double)__fsub_rn(target, php));
+                s_start[r] = r == 0 ? 0 : (s_cur[r - 1] + p2 + 1) >> 1;  // round((a+b)*0.5), half away from zero
             }
+            if (tid == 0) s_start[npk] = half;
             __syncthreads();   // (D) rotations and region starts complete; all reads of the old state are done
             // lock every bin to its region's peak (:685-699); the region of bin b0 is that of the peak before b0 or of the
             // first peak at/after b0, and at most kMaxOwn more regions start inside the thread's bins
@@ -979,7 +979,7 @@ void launch_phase_core(const DevPlan &p, const DevRows &g, int coremode, const S
     const int streams = g.rows / g.channels;
     if (coremode == 1 && (p.N == 512 || p.N == 1024 || p.N == 2048 || p.N == 4096 || p.N == 8192)) {
         const int E = p.N == 8192 ? 8 : 4;
-        const size_t sm = sizeof(float) * ((size_t)p.half + 8 + (size_t)2 * g.channels * p.half + (size_t)4 * g.maxpk + 1 + 32 + 8);
+        const size_t sm = sizeof(float) * ((size_t)2 * p.half + 8 + (size_t)2 * g.channels * p.half + (size_t)4 * g.maxpk + 1 + 32 + 8);
         if (E == 4) k_phase_lock_t<4><<<streams, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
         else k_phase_lock_t<8><<<streams, p.half / 8, sm, st>>>(p, g, recs, recs_base, k0, nframes);
         return;
