@@ -652,7 +652,8 @@ __global__ void k_synthesise(const DevPlan p, const DevRows g, const float *__re
 struct SynthBinLoader {
     const DevPlan &p;
     const float *__restrict__ gmag, *__restrict__ gph, *__restrict__ cmag, *__restrict__ cph;
-    __device__ __forceinline__ float2 operator()(int i) const {
+    // magnitude (before the 1/N scale) and phase of packed bin i after the mode's spectral modification
+    __device__ __forceinline__ float2 load(int i) const {
         const int hs = p.half;
         float m, ph;
         if (cmag != nullptr) {  // modifySliceVocoder (:755-776)
@@ -684,11 +685,16 @@ struct SynthBinLoader {
         } else {
             m = gmag[i]; ph = gph[i];
         }
-        m = __fmul_rn(m, p.inv_n);
+        return make_float2(m, ph);
+    }
+    // 1/N scale (:1024) and polar -> cartesian (FFT.cc:2711-2721)
+    __device__ __forceinline__ float2 finish(float2 mp) const {
+        const float m = __fmul_rn(mp.x, p.inv_n);
         float sn, cs;
-        sincosf(ph, &sn, &cs);
+        sincosf(mp.y, &sn, &cs);
         return make_float2(m * cs, m * sn);
     }
+    __device__ __forceinline__ float2 operator()(int i) const { return finish(load(i)); }
 };
 
 template <int N>
@@ -710,9 +716,21 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
         const int64_t co = (int64_t)(k - g.aux_base) * p.Hp;
         const SynthBinLoader bin{p, g.mag + so, g.phase + so, car_mag ? car_mag + co : nullptr, car_mag ? car_phase + co : nullptr};
         const float2 *__restrict__ stw = p.stw_inv;
-        for (int kk = t; kk <= NC / 2; kk += T) {  // inverse real-FFT pre-pass (kiss_fftr.c:123-159)
-            const float2 fk = bin(kk);
-            const float2 fq = bin(NC - kk);
+        // inverse real-FFT pre-pass (kiss_fftr.c:123-159).  All loads of the thread's bins are issued before any of the
+        // (long) sincos evaluations so their latency overlaps.
+        constexpr int Q = (NC / 2) / T;
+        float2 lo[Q], hi[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int kk = t + T * q;
+            lo[q] = bin.load(kk);
+            hi[q] = bin.load(NC - kk);
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const int kk = t + T * q;
+            const float2 fk = bin.finish(lo[q]);
+            const float2 fq = bin.finish(hi[q]);
             if (kk == 0) {
                 buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk.x + fq.x, fk.x - fq.x);
             } else {
@@ -721,9 +739,17 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
                 const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
                 const float2 a = cadd_rn(fek, fok);
                 const float2 b = csub_rn(fek, fok);
-                if (kk != NC - kk) buf[fft_pad(fft_slot_of_input<NC>(kk))] = a;
+                buf[fft_pad(fft_slot_of_input<NC>(kk))] = a;
                 buf[fft_pad(fft_slot_of_input<NC>(NC - kk))] = make_float2(b.x, -b.y);
             }
+        }
+        if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)
+            const float2 fk = bin(NC / 2);
+            const float2 fnkc = make_float2(fk.x, -fk.y);
+            const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
+            const float2 fok = cmul_rn(d, __ldg(&stw[NC / 2]));
+            const float2 b = csub_rn(fek, fok);
+            buf[fft_pad(fft_slot_of_input<NC>(NC / 2))] = make_float2(b.x, -b.y);
         }
     }
     frame_sync<T>(group);
