@@ -123,19 +123,28 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
     const int row = active ? fid / nf : 0, f = active ? fid % nf : 0;
     if (active) {
         const long k = k0 + f;
-        const float *__restrict__ x = g.in + (int64_t)row * g.in_stride;
         const int64_t start = (int64_t)k * p.hop;
-        const int64_t nvalid = g.n_in[row];
+        const float *__restrict__ x = g.in + (int64_t)row * g.in_stride + (start - g.in_base);
+        const int64_t left = g.n_in[row] - start;
+        const int valid = left < 0 ? 0 : (left > N ? N : (int)left);   // samples of this frame that exist; the rest are zeros
         const float2 *__restrict__ w2 = (const float2 *)p.window;
-        // gather + Hann + fftshift + KissFFT input permutation, one complex (two consecutive samples) at a time
-#pragma unroll 4
-        for (int cc = t; cc < NC; cc += T) {
-            const int64_t gi = start + 2 * cc;
-            const float x0 = gi < nvalid ? x[gi - g.in_base] : 0.f;
-            const float x1 = gi + 1 < nvalid ? x[gi + 1 - g.in_base] : 0.f;
-            const float2 w = __ldg(&w2[cc]);
-            const int c = (cc + NC / 2) & (NC - 1);   // fftshift moves sample i to (i + N/2) mod N, i.e. complex cc to cc + NC/2
-            buf[fft_pad(fft_slot_of_input<NC>(c))] = make_float2(__fmul_rn(x0, w.x), __fmul_rn(x1, w.y));
+        // gather + Hann + fftshift + KissFFT input permutation, one complex (two consecutive samples) at a time.  Complex
+        // cc = t + T*i lands (after the fftshift by NC/2) at slot perm(t) | perm((T*i + NC/2) mod NC): the permutation is a
+        // bit permutation and the two parts have disjoint bits, and the padded position is additive in the two parts, so
+        // every store is base + compile-time constant.
+        const int base = fft_pad(fft_slot_of_input<NC>(t));
+        float x0[16], x1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int s0 = 2 * (t + T * i);
+            x0[i] = s0 < valid ? x[s0] : 0.f;
+            x1[i] = s0 + 1 < valid ? x[s0 + 1] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float2 w = __ldg(&w2[t + T * i]);
+            const int K = fft_pad(fft_slot_of_input<NC>((T * i + NC / 2) & (NC - 1)));
+            buf[base + K] = make_float2(__fmul_rn(x0[i], w.x), __fmul_rn(x1[i], w.y));
         }
     }
     frame_sync<T>(group);
@@ -153,29 +162,46 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
     float *__restrict__ mag = g.mag + ((int64_t)row * g.F + f) * p.Hp;
     float *__restrict__ ph = g.phase + ((int64_t)row * g.F + f) * p.Hp;
     const float2 *__restrict__ stw = p.stw_fwd;
-    for (int kk = t; kk <= NC / 2; kk += T) {
+    constexpr int Q = (NC / 2) / T;
+    const int pa = fft_pad(t), pb = fft_pad((T - t) & (T - 1));   // padded positions are additive in (t, T*q)
+    float2 fa[Q], fb[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        fa[q] = buf[pa + fft_pad(T * q)];
+        // NC - (t + T*q) = T*(15-q) + (T-t) for t > 0, T*(16-q) for t == 0 (q == 0 pairs DC with itself: handled below)
+        fb[q] = buf[pb + (t == 0 ? fft_pad((T * (16 - q)) & (NC - 1)) : fft_pad(T * (15 - q)))];
+    }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const int kk = t + T * q;
         if (kk == 0) {
-            const float2 z = buf[fft_pad(0)];
+            const float2 z = fa[0];
             const float dc = __fadd_rn(z.x, z.y), ny = __fsub_rn(z.x, z.y);
             mag[0] = __fsqrt_rn(__fadd_rn(__fmul_rn(dc, dc), 0.f));
             ph[0] = pv_atan2f(0.f, dc);
             mag[NC] = __fsqrt_rn(__fadd_rn(__fmul_rn(ny, ny), 0.f));
             ph[NC] = pv_atan2f(0.f, ny);
         } else {
-            const float2 fpk = buf[fft_pad(kk)];
-            const float2 fq = buf[fft_pad(NC - kk)];
-            const float2 fpnk = make_float2(fq.x, -fq.y);
+            const float2 fpk = fa[q];
+            const float2 fpnk = make_float2(fb[q].x, -fb[q].y);
             const float2 f1k = cadd_rn(fpk, fpnk), f2k = csub_rn(fpk, fpnk);
             const float2 tw = cmul_rn(f2k, __ldg(&stw[kk]));
             const float ar = __fmul_rn(__fadd_rn(f1k.x, tw.x), 0.5f), ai = __fmul_rn(__fadd_rn(f1k.y, tw.y), 0.5f);
             const float br = __fmul_rn(__fsub_rn(f1k.x, tw.x), 0.5f), bi = __fmul_rn(__fsub_rn(tw.y, f1k.y), 0.5f);
-            if (kk != NC - kk) {  // bin NC/2 is written twice by the reference; the second write wins
-                mag[kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
-                ph[kk] = pv_atan2f_fast(ai, ar);
-            }
+            mag[kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
+            ph[kk] = pv_atan2f_fast(ai, ar);
             mag[NC - kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
             ph[NC - kk] = pv_atan2f_fast(bi, br);
         }
+    }
+    if (t == 0) {   // bin NC/2 pairs with itself; the reference writes it twice and the second write wins (kiss_fftr.c:116-119)
+        const float2 fpk = buf[fft_pad(NC / 2)];
+        const float2 fpnk = make_float2(fpk.x, -fpk.y);
+        const float2 f1k = cadd_rn(fpk, fpnk), f2k = csub_rn(fpk, fpnk);
+        const float2 tw = cmul_rn(f2k, __ldg(&stw[NC / 2]));
+        const float br = __fmul_rn(__fsub_rn(f1k.x, tw.x), 0.5f), bi = __fmul_rn(__fsub_rn(tw.y, f1k.y), 0.5f);
+        mag[NC / 2] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+        ph[NC / 2] = pv_atan2f_fast(bi, br);
     }
 }
 
@@ -719,6 +745,7 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
         // inverse real-FFT pre-pass (kiss_fftr.c:123-159).  All loads of the thread's bins are issued before any of the
         // (long) sincos evaluations so their latency overlaps.
         constexpr int Q = (NC / 2) / T;
+        const int sa = fft_pad(fft_slot_of_input<NC>(t)), sb = fft_pad(fft_slot_of_input<NC>((T - t) & (T - 1)));
         float2 lo[Q], hi[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -739,8 +766,10 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
                 const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
                 const float2 a = cadd_rn(fek, fok);
                 const float2 b = csub_rn(fek, fok);
-                buf[fft_pad(fft_slot_of_input<NC>(kk))] = a;
-                buf[fft_pad(fft_slot_of_input<NC>(NC - kk))] = make_float2(b.x, -b.y);
+                // slot(t + T*q) = slot(t) | slot(T*q) and the padded position is additive (see k_analyse_t)
+                buf[sa + fft_pad(fft_slot_of_input<NC>(T * q))] = a;
+                buf[sb + (t == 0 ? fft_pad(fft_slot_of_input<NC>((T * (16 - q)) & (NC - 1))) : fft_pad(fft_slot_of_input<NC>(T * (15 - q))))] =
+                    make_float2(b.x, -b.y);
             }
         }
         if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)
