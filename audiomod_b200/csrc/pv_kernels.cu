@@ -110,7 +110,7 @@ __global__ void k_analyse(const DevPlan p, const DevRows g, long k0) {
 // max(T, 256) threads handles 256/T consecutive frames of the chunk.
 // ------------------------------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(const DevPlan p, const DevRows g, long k0, int nf, int total) {
+__global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256), 4) k_analyse_t(const DevPlan p, const DevRows g, long k0, int nf, int total) {
     constexpr int NC = N / 2;
     using S = FftShape<NC>;
     constexpr int T = S::kThreads;
