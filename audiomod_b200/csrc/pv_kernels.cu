@@ -21,6 +21,9 @@
 #include "pv_fft.cuh"
 #include "pv_math.cuh"
 
+// out-of-line copy of the general atan2f for the rare arguments the fast path rejects (keeps the hot kernels small)
+__device__ __noinline__ float pv_atan2f_rare(float y, float x) { return pv_atan2f(y, x); }
+
 namespace pvgpu {
 
 // All butterfly stages of the nc-point complex FFT, in place in shared memory (data already permuted).
@@ -110,7 +113,7 @@ __global__ void k_analyse(const DevPlan p, const DevRows g, long k0) {
 // max(T, 256) threads handles 256/T consecutive frames of the chunk.
 // ------------------------------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256), 4) k_analyse_t(const DevPlan p, const DevRows g, long k0, int nf, int total) {
+__global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(const DevPlan p, const DevRows g, long k0, int nf, int total) {
     constexpr int NC = N / 2;
     using S = FftShape<NC>;
     constexpr int T = S::kThreads;
@@ -164,35 +167,29 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256), 4) k_analyse_t(
     const float2 *__restrict__ stw = p.stw_fwd;
     constexpr int Q = (NC / 2) / T;
     const int pa = fft_pad(t), pb = fft_pad((T - t) & (T - 1));   // padded positions are additive in (t, T*q)
-    float2 fa[Q], fb[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        fa[q] = buf[pa + fft_pad(T * q)];
-        // NC - (t + T*q) = T*(15-q) + (T-t) for t > 0, T*(16-q) for t == 0 (q == 0 pairs DC with itself: handled below)
-        fb[q] = buf[pb + (t == 0 ? fft_pad((T * (16 - q)) & (NC - 1)) : fft_pad(T * (15 - q)))];
-    }
-#pragma unroll
+    // rolled on purpose: the body holds two atan2f and two sqrtf expansions, and unrolling it 8x makes the kernel
+    // several times larger than the instruction cache
+#pragma unroll 1
     for (int q = 0; q < Q; ++q) {
         const int kk = t + T * q;
+        const float2 fpk = buf[pa + fft_pad(T * q)];
+        // NC - (t + T*q) = T*(15-q) + (T-t) for t > 0, T*(16-q) for t == 0 (q == 0 pairs DC with itself)
+        const float2 fq = buf[pb + (t == 0 ? fft_pad((T * (16 - q)) & (NC - 1)) : fft_pad(T * (15 - q)))];
+        float ar, ai, br, bi;
         if (kk == 0) {
-            const float2 z = fa[0];
-            const float dc = __fadd_rn(z.x, z.y), ny = __fsub_rn(z.x, z.y);
-            mag[0] = __fsqrt_rn(__fadd_rn(__fmul_rn(dc, dc), 0.f));
-            ph[0] = pv_atan2f(0.f, dc);
-            mag[NC] = __fsqrt_rn(__fadd_rn(__fmul_rn(ny, ny), 0.f));
-            ph[NC] = pv_atan2f(0.f, ny);
+            ar = __fadd_rn(fpk.x, fpk.y); ai = 0.f;   // DC
+            br = __fsub_rn(fpk.x, fpk.y); bi = 0.f;   // Nyquist
         } else {
-            const float2 fpk = fa[q];
-            const float2 fpnk = make_float2(fb[q].x, -fb[q].y);
+            const float2 fpnk = make_float2(fq.x, -fq.y);
             const float2 f1k = cadd_rn(fpk, fpnk), f2k = csub_rn(fpk, fpnk);
             const float2 tw = cmul_rn(f2k, __ldg(&stw[kk]));
-            const float ar = __fmul_rn(__fadd_rn(f1k.x, tw.x), 0.5f), ai = __fmul_rn(__fadd_rn(f1k.y, tw.y), 0.5f);
-            const float br = __fmul_rn(__fsub_rn(f1k.x, tw.x), 0.5f), bi = __fmul_rn(__fsub_rn(tw.y, f1k.y), 0.5f);
-            mag[kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
-            ph[kk] = pv_atan2f_fast(ai, ar);
-            mag[NC - kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
-            ph[NC - kk] = pv_atan2f_fast(bi, br);
+            ar = __fmul_rn(__fadd_rn(f1k.x, tw.x), 0.5f); ai = __fmul_rn(__fadd_rn(f1k.y, tw.y), 0.5f);
+            br = __fmul_rn(__fsub_rn(f1k.x, tw.x), 0.5f); bi = __fmul_rn(__fsub_rn(tw.y, f1k.y), 0.5f);
         }
+        mag[kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
+        ph[kk] = pv_atan2f_fast(ai, ar);
+        mag[NC - kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+        ph[NC - kk] = pv_atan2f_fast(bi, br);
     }
     if (t == 0) {   // bin NC/2 pairs with itself; the reference writes it twice and the second write wins (kiss_fftr.c:116-119)
         const float2 fpk = buf[fft_pad(NC / 2)];
@@ -746,30 +743,34 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
         // (long) sincos evaluations so their latency overlaps.
         constexpr int Q = (NC / 2) / T;
         const int sa = fft_pad(fft_slot_of_input<NC>(t)), sb = fft_pad(fft_slot_of_input<NC>((T - t) & (T - 1)));
-        float2 lo[Q], hi[Q];
+        // rolled in groups of two pairs: four independent loads in flight per step without unrolling the (large) sincos
+        // expansion 16 times, which would not fit the instruction cache
+#pragma unroll 1
+        for (int q0 = 0; q0 < Q; q0 += 2) {
+            float2 lo[2], hi[2];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int kk = t + T * q;
-            lo[q] = bin.load(kk);
-            hi[q] = bin.load(NC - kk);
-        }
+            for (int u = 0; u < 2; ++u) {
+                lo[u] = bin.load(t + T * (q0 + u));
+                hi[u] = bin.load(NC - (t + T * (q0 + u)));
+            }
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const int kk = t + T * q;
-            const float2 fk = bin.finish(lo[q]);
-            const float2 fq = bin.finish(hi[q]);
-            if (kk == 0) {
-                buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk.x + fq.x, fk.x - fq.x);
-            } else {
-                const float2 fnkc = make_float2(fq.x, -fq.y);
-                const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
-                const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
-                const float2 a = cadd_rn(fek, fok);
-                const float2 b = csub_rn(fek, fok);
-                // slot(t + T*q) = slot(t) | slot(T*q) and the padded position is additive (see k_analyse_t)
-                buf[sa + fft_pad(fft_slot_of_input<NC>(T * q))] = a;
-                buf[sb + (t == 0 ? fft_pad(fft_slot_of_input<NC>((T * (16 - q)) & (NC - 1))) : fft_pad(fft_slot_of_input<NC>(T * (15 - q))))] =
-                    make_float2(b.x, -b.y);
+            for (int u = 0; u < 2; ++u) {
+                const int q = q0 + u, kk = t + T * q;
+                const float2 fk = bin.finish(lo[u]);
+                const float2 fq = bin.finish(hi[u]);
+                if (kk == 0) {
+                    buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk.x + fq.x, fk.x - fq.x);
+                } else {
+                    const float2 fnkc = make_float2(fq.x, -fq.y);
+                    const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
+                    const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
+                    const float2 a = cadd_rn(fek, fok);
+                    const float2 b = csub_rn(fek, fok);
+                    // slot(t + T*q) = slot(t) | slot(T*q) and the padded position is additive (see k_analyse_t)
+                    buf[sa + fft_pad(fft_slot_of_input<NC>(T * q))] = a;
+                    buf[sb + (t == 0 ? fft_pad(fft_slot_of_input<NC>((T * (16 - q)) & (NC - 1))) : fft_pad(fft_slot_of_input<NC>(T * (15 - q))))] =
+                        make_float2(b.x, -b.y);
+                }
             }
         }
         if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)

@@ -89,6 +89,9 @@ PV_HD float pv_atanf(float x) {
     return hx < 0 ? -r : r;
 }
 
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ float pv_atan2f_rare(float y, float x);
+#endif
 PV_HD float pv_atan2f(float y, float x) {
     const float tiny = 1.0e-30f;
     const float pi_o_4 = PV_I2F(0x3f490fdb), pi_o_2 = PV_I2F(0x3fc90fdb), pi = PV_I2F(0x40490fdb), pi_lo = PV_I2F(0xb3bbbd2e);
@@ -147,10 +150,15 @@ PV_HD float pv_atan2f_fast(float y, float x) {
     const int k = (iy - ix) >> 23;
     // iy-1 / ix-1 as unsigned: rejects zero and inf/NaN with one compare each
     const bool common = ((uint32_t)(iy - 1) < 0x7f7fffffu) & ((uint32_t)(ix - 1) < 0x7f7fffffu) & (hx != 0x3f800000) & (k <= 60) & (k >= -60);
-    if (!common) return pv_atan2f(y, x);
+#if defined(__CUDA_ARCH__)
+#define PV_ATAN2_RARE pv_atan2f_rare
+#else
+#define PV_ATAN2_RARE pv_atan2f
+#endif
+    if (!common) return PV_ATAN2_RARE(y, x);
     const float q = PV_I2F(PV_F2I(PV_DIV(y, x)) & 0x7fffffff);  // fabsf(y/x)
     const int32_t iq = PV_F2I(q);
-    if (iq >= 0x4c000000) return pv_atan2f(y, x);                // |y/x| >= 2^25 (or the quotient overflowed)
+    if (iq >= 0x4c000000) return PV_ATAN2_RARE(y, x);            // |y/x| >= 2^25 (or the quotient overflowed)
     float a, b, c, d, hi, lo;
     if (iq < 0x3f300000) {          // < 11/16   (also covers < 7/16, where these are unused)
         a = 2.0f; b = -1.0f; c = 1.0f; d = 2.0f; hi = PV_I2F(0x3eed6338); lo = PV_I2F(0x31ac3769);
