@@ -817,15 +817,13 @@ constexpr int kOlaMaxFrames = 96;   // frames overlapping them
 
 
 struct OlaTables {
-    int64_t res_off[kOlaMaxSlices + 1];   // resampler-stream offset of each table slice (+ end sentinel)
-    int64_t ola_off[kOlaMaxSlices];
-    int jlo[kOlaMaxSlices];
+    int res_rel[kOlaMaxSlices + 1];       // start of each table slice in the normalised stream, relative to u_lo (+ end sentinel)
+    int ola_rel[kOlaMaxSlices];           // its OLA position relative to ola_base
+    int j0[kOlaMaxSlices];                // first overlapping frame, relative to jmin
+    int out_rel[kOlaMaxSlices];           // run slices only: output position relative to the run's first, and how many
+    int n_store[kOlaMaxSlices];           //   samples may be stored (n_write clipped by the row's n_out)
     int fr_off[kOlaMaxFrames];            // ola_off of frame (jmin + i) relative to ola_base
-    int fr_slot[kOlaMaxFrames];           // its slot in the frame ring
-    int out_pref[kOlaMaxSlices + 1];      // flattened output index of each run slice
-    long kmin, jmin;
-    int nsl, nfr;
-    int64_t ola_base, u_lo, u_hi;
+    int fr_pos[kOlaMaxFrames];            // slot * N of that frame in the ring
 };
 
 template <int OV>   // sinc-table oversampling of the interpolated resampler mode; 0 = direct table or no resampler
@@ -845,43 +843,37 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
     const int tid = threadIdx.x;
     if (p.rs_active) for (int i = tid; i < L; i += blockDim.x) s_in[i - L] = 0.f;
 
-    if (tid == 0) {
-        // slices whose normalised samples are needed: the run plus the resampler history before it
-        const SliceRec &ra = recs[ka - recs_base];
-        const int64_t u_lo = p.rs_active ? ra.res_off + ra.rs_last - L + 1 : ra.res_off;
-        long kmin = ka;
-        while (kmin > recs_base && kmin > 0 && recs[kmin - recs_base].res_off > u_lo && ka - kmin < kOlaMaxSlices - run - 1) --kmin;
-        int n = 0, pref = 0;
-        long jmin = recs[kmin - recs_base].jlo;
-        for (long k = kmin; k < kb; ++k, ++n) {
-            const SliceRec &r = recs[k - recs_base];
-            T.res_off[n] = r.res_off;
-            T.ola_off[n] = r.ola_off;
-            T.jlo[n] = r.jlo;
-            if (k >= ka) {
-                T.out_pref[k - ka] = pref;
-                int n_store = (r.flags & 1) ? 0 : r.n_write;
-                if (r.out_off + n_store > g.n_out[row]) n_store = (int)max((int64_t)0, g.n_out[row] - r.out_off);
-                pref += n_store;
-            }
-        }
-        T.out_pref[kb - ka] = pref;
-        const SliceRec &rl = recs[kb - 1 - recs_base];
-        const int64_t u_hi = rl.res_off + ((rl.flags & 1) ? 0 : rl.consumed);
-        T.res_off[n] = u_hi;
-        T.kmin = kmin; T.jmin = jmin; T.nsl = n;
-        T.ola_base = recs[jmin - recs_base].ola_off;
-        int nfr = (int)(kb - jmin);
-        if (nfr > kOlaMaxFrames) nfr = kOlaMaxFrames;   // cannot happen for schedules the host accepts (halo check)
-        T.nfr = nfr;
-        T.u_lo = u_lo < 0 ? 0 : u_lo;
-        T.u_hi = u_hi;
+    // slices whose normalised samples are needed: the run plus the resampler history before it (every thread walks the
+    // few records back; the loads are uniform and cached)
+    const int N = p.N;
+    const SliceRec *__restrict__ rr = recs - recs_base;
+    const int64_t u_lo_raw = p.rs_active ? rr[ka].res_off + rr[ka].rs_last - L + 1 : rr[ka].res_off;
+    long kmin = ka;
+    while (kmin > recs_base && kmin > 0 && rr[kmin].res_off > u_lo_raw && ka - kmin < kOlaMaxSlices - run - 1) --kmin;
+    const long jmin = rr[kmin].jlo;
+    const int nsl = (int)(kb - kmin);
+    const int nfr = min((int)(kb - jmin), kOlaMaxFrames);   // the host's halo check keeps kb - jmin within the table
+    const int64_t ola_base = rr[jmin].ola_off;
+    const int64_t u_lo = u_lo_raw < 0 ? 0 : u_lo_raw;
+    const int64_t u_hi = rr[kb - 1].res_off + ((rr[kb - 1].flags & 1) ? 0 : rr[kb - 1].consumed);
+    const int span = (int)min(u_hi - u_lo, (int64_t)max_in);
+    const int64_t out_first = rr[ka].out_off;
+    const int64_t row_limit = g.n_out[row];
+    for (int n = tid; n < nsl; n += blockDim.x) {
+        const SliceRec &r = rr[kmin + n];
+        T.res_rel[n] = (int)(r.res_off - u_lo);
+        T.ola_rel[n] = (int)(r.ola_off - ola_base);
+        T.j0[n] = (int)(r.jlo - jmin);
+        int n_store = (r.flags & 1) ? 0 : r.n_write;
+        if (r.out_off + n_store > row_limit) n_store = (int)max((int64_t)0, row_limit - r.out_off);
+        T.out_rel[n] = (int)(r.out_off - out_first);
+        T.n_store[n] = n_store;
     }
-    __syncthreads();
-    for (int i = tid; i < T.nfr; i += blockDim.x) {
-        const long j = T.jmin + i;
-        T.fr_off[i] = (int)(recs[j - recs_base].ola_off - T.ola_base);
-        T.fr_slot[i] = (int)(j % g.Fr);
+    if (tid == 0) T.res_rel[nsl] = span;
+    for (int i = tid; i < nfr; i += blockDim.x) {
+        const long j = jmin + i;
+        T.fr_off[i] = (int)(rr[j].ola_off - ola_base);
+        T.fr_pos[i] = (int)(j % g.Fr) * N;
     }
     if (quad) {
         const float4 *__restrict__ tab4 = p.rs_quads;   // host-built (tab[e-2], tab[e-1], tab[e], tab[e+1])
@@ -890,33 +882,29 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
     __syncthreads();
 
     // ---- normalised overlap-add stream for [u_lo, u_hi) ----
-    const int N = p.N;
     const float *__restrict__ fr = g.frames + (int64_t)row * g.Fr * N;
-    const int64_t u_lo = T.u_lo, u_hi = T.u_hi;
-    const int span = (int)min(u_hi - u_lo, (int64_t)max_in);
-    const int nsl = T.nsl;
+    const float *__restrict__ nrm = norm + (ola_base - norm_base);
     const int64_t row_out = (int64_t)row * g.out_stride - g.out_base;
-    for (int e = tid; e < span; e += blockDim.x) {
-        const int64_t u = u_lo + e;
-        int lo = 0, hi = nsl;   // last table slice with res_off <= u (dropped / empty slices share an offset: take the last)
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (T.res_off[mid] <= u) lo = mid; else hi = mid; }
-        const int64_t t = T.ola_off[lo] + (u - T.res_off[lo]);
-        const int trel = (int)(t - T.ola_base);
-        const int j0 = (int)(T.jlo[lo] - T.jmin), j1 = (int)(T.kmin + lo - T.jmin);
-        float acc = 0.f;
-        for (int j = j0; j <= j1; ++j) {
-            const int off = trel - T.fr_off[j];
-            if (off < N) acc += fr[(int64_t)T.fr_slot[j] * N + off];
-        }
-        const float v = acc / norm[t - norm_base];
-        if (p.rs_active) {
-            s_in[e] = v;
-        } else {
-            // no resampling: res_off == out_off and the sample goes straight out (n_write / n_out clip)
-            const int ks = (int)(T.kmin + lo - ka);
-            if (ks >= 0) {
-                const int i = (int)(u - T.res_off[lo]);
-                if (i < T.out_pref[ks + 1] - T.out_pref[ks]) g.out[row_out + recs[ka + ks - recs_base].out_off + i] = v;
+    const int first_run_slice = (int)(ka - kmin);
+    {
+        int sl = 0;
+        for (int e = tid; e < span; e += blockDim.x) {
+            while (T.res_rel[sl + 1] <= e) ++sl;   // last table slice starting at or before e (dropped slices share an offset)
+            const int i = e - T.res_rel[sl];
+            const int trel = T.ola_rel[sl] + i;
+            const int j1 = (int)(kmin - jmin) + sl;
+            float acc = 0.f;
+#pragma unroll 4
+            for (int j = T.j0[sl]; j <= j1; ++j) {
+                const int off = trel - T.fr_off[j];
+                if (off < N) acc += fr[T.fr_pos[j] + off];
+            }
+            const float v = acc / nrm[trel];
+            if (p.rs_active) {
+                s_in[e] = v;
+            } else if (sl >= first_run_slice && i < T.n_store[sl]) {
+                // no resampling: the normalised sample is the output sample (n_write / n_out clip)
+                g.out[row_out + out_first + T.out_rel[sl] + i] = v;
             }
         }
     }
@@ -935,6 +923,7 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
     float *__restrict__ orow = g.out + row_out + hdr.out_first;
     const int64_t out_limit = g.n_out[row] - hdr.out_first;
     const int in_shift = (int)(hdr.u_lo - u_lo) - kResPad;   // hdr.u_lo == u_lo; entries are biased by kResPad
+    (void)out_first;
     for (int e = tid; e < hdr.padded; e += blockDim.x) {
         const unsigned ent = __ldg(&ent_tab[e]);
         int bucket = 0;
