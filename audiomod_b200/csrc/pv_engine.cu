@@ -264,7 +264,7 @@ struct Pipeline {
                 ent.insert(ent.end(), be[q].begin(), be[q].end());
                 frac.insert(frac.end(), bf[q].begin(), bf[q].end());
                 pos += (int)be[q].size();
-                while (pos & 31) { ent.push_back(0xffffffffu); frac.push_back(0.f); ++pos; }
+                while (pos % kResBlock) { ent.push_back(0xffffffffu); frac.push_back(0.f); ++pos; }
             }
             for (int q = nb; q <= kMaxBuckets; ++q) hdr.start[q] = pos;
             hdr.padded = pos;

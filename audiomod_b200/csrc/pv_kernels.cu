@@ -924,41 +924,63 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
     const int64_t out_limit = g.n_out[row] - hdr.out_first;
     const int in_shift = (int)(hdr.u_lo - u_lo) - kResPad;   // hdr.u_lo == u_lo; entries are biased by kResPad
     (void)out_first;
-    for (int e = tid; e < hdr.padded; e += blockDim.x) {
-        const unsigned ent = __ldg(&ent_tab[e]);
+    // kResBlock entries (one phase) per warp step, kResPerThread outputs per thread: the quad of a tap is loaded once and
+    // feeds 4 x kResPerThread FMAs (a 128-bit shared load costs four wavefronts even when it is a broadcast)
+    const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    for (int blk = warp * kResBlock; blk < hdr.padded; blk += nwarp * kResBlock) {
         int bucket = 0;
 #pragma unroll
-        for (int q = 1; q < nb; ++q) bucket += hdr.start[q] <= (e & ~31);   // warp-uniform
-        if (ent == 0xffffffffu || (int64_t)(ent & 0xffffu) >= out_limit) continue;
-        const float *xs = s_in + ((int)(ent >> 16) + in_shift);   // tap 0; may reach into the zero history before s_in[0]
-        float sum;
+        for (int q = 1; q < nb; ++q) bucket += hdr.start[q] <= blk;   // warp-uniform
+        unsigned ent[kResPerThread];
+        const float *xs[kResPerThread];
+        bool live[kResPerThread];
+#pragma unroll
+        for (int u = 0; u < kResPerThread; ++u) {
+            ent[u] = __ldg(&ent_tab[blk + lane + 32 * u]);
+            live[u] = ent[u] != 0xffffffffu && (int64_t)(ent[u] & 0xffffu) < out_limit;
+            // tap 0; may reach into the zero history before s_in[0]; dead entries read (and discard) from a safe place
+            xs[u] = live[u] ? s_in + ((int)(ent[u] >> 16) + in_shift) : s_in;
+        }
         if (OV == 0) {
-            sum = 0.f;
-            const float *__restrict__ tt = p.rs_table + (size_t)__float_as_uint(__ldg(&frac_tab[e])) * L;
-            for (int j = 0; j < L; ++j) sum += xs[j] * __ldg(&tt[j]);
+#pragma unroll
+            for (int u = 0; u < kResPerThread; ++u) {
+                if (!live[u]) continue;
+                float sum = 0.f;
+                const float *__restrict__ tt = p.rs_table + (size_t)__float_as_uint(__ldg(&frac_tab[blk + lane + 32 * u])) * L;
+                for (int j = 0; j < L; ++j) sum += xs[u][j] * __ldg(&tt[j]);
+                orow[ent[u] & 0xffffu] = sum;
+            }
         } else {
-            const float frac = __ldg(&frac_tab[e]);
             const float4 *q = s_quad + 4 + OV - bucket;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            float acc[kResPerThread][4];
+#pragma unroll
+            for (int u = 0; u < kResPerThread; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
             for (int j = 0; j < L; j += 4) {   // filt_len is a multiple of 4 (resample.c:712)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float v = xs[j + u];
-                    const float4 tq = q[(j + u) * OV];
-                    a0 += v * tq.x;
-                    a1 += v * tq.y;
-                    a2 += v * tq.z;
-                    a3 += v * tq.w;
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float4 tq = q[(j + jj) * OV];
+#pragma unroll
+                    for (int u = 0; u < kResPerThread; ++u) {
+                        const float v = xs[u][j + jj];
+                        acc[u][0] += v * tq.x;
+                        acc[u][1] += v * tq.y;
+                        acc[u][2] += v * tq.z;
+                        acc[u][3] += v * tq.w;
+                    }
                 }
             }
-            // cubic_coef (resample.c:339-351)
-            const float i0 = -0.16667f * frac + 0.16667f * frac * frac * frac;
-            const float i1 = frac + 0.5f * frac * frac - 0.5f * frac * frac * frac;
-            const float i3 = -0.33333f * frac + 0.5f * frac * frac - 0.16667f * frac * frac * frac;
-            const float i2 = (float)(1. - i0 - i1 - i3);
-            sum = (i0 * a0) + (i1 * a1) + (i2 * a2) + (i3 * a3);
+#pragma unroll
+            for (int u = 0; u < kResPerThread; ++u) {
+                if (!live[u]) continue;
+                const float frac = __ldg(&frac_tab[blk + lane + 32 * u]);
+                // cubic_coef (resample.c:339-351)
+                const float i0 = -0.16667f * frac + 0.16667f * frac * frac * frac;
+                const float i1 = frac + 0.5f * frac * frac - 0.5f * frac * frac * frac;
+                const float i3 = -0.33333f * frac + 0.5f * frac * frac - 0.16667f * frac * frac * frac;
+                const float i2 = (float)(1. - i0 - i1 - i3);
+                orow[ent[u] & 0xffffu] = (i0 * acc[u][0]) + (i1 * acc[u][1]) + (i2 * acc[u][2]) + (i3 * acc[u][3]);
+            }
         }
-        orow[ent & 0xffffu] = sum;
     }
 }
 

@@ -60,10 +60,12 @@ void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table /
 void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase /*[slices][Hp] indexed by absolute slice, or null*/,
                        long k0, int nframes, cudaStream_t st);
 // Host-built work list of the resampler for one run of slices (see k_ola_resample): the run's outputs bucketed by
-// sinc-table phase, output order inside a bucket, buckets padded to multiples of 32.  Entry = (tap-0 position relative to
+// sinc-table phase, output order inside a bucket, buckets padded to multiples of kResBlock.  Entry = (tap-0 position relative to
 // u_lo + kResPad) << 16 | (output position relative to out_first); 0xffffffff = padding.  rs_frac holds the cubic
 // interpolation fraction of each entry (interpolated mode) or the table phase as raw bits (direct mode).
 constexpr int kMaxBuckets = 8;      // resampler table phases (oversample <= 8 at quality 4)
+constexpr int kResPerThread = 4;    // outputs a thread of k_ola_resample accumulates at once
+constexpr int kResBlock = 32 * kResPerThread;   // entries a warp takes per step; buckets are padded to this
 constexpr int kResPad = 1024;       // bias that keeps the packed tap-0 offset non-negative at the start of a stream
 struct ResampleRun {
     int64_t u_lo;        // first normalised-stream position the run reads (clipped to 0)
