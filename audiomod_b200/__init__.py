@@ -2,8 +2,8 @@
 from .phasevocoder import (CONSTANT, FORMANT_PRESERVE, GENDER_CHANGE, INT_RATIO, NORMAL_PV, NORMAL_SHIFT, NORMAL_STRETCH,
                            PHASE_LOCKED, ROBOTIC, VOCODER_CHORD, VOCODER_ROSENBERG, WHISPER, PhaseVocoderBatch, describe, plan_counts,
                            phasevocoder)
-from ._lib import PvgpuError
+from ._lib import F32, S16, PvgpuError
 
-__all__ = ["phasevocoder", "PhaseVocoderBatch", "describe", "plan_counts", "PvgpuError", "CONSTANT", "NORMAL_SHIFT", "GENDER_CHANGE",
+__all__ = ["phasevocoder", "PhaseVocoderBatch", "describe", "plan_counts", "PvgpuError", "F32", "S16", "CONSTANT", "NORMAL_SHIFT", "GENDER_CHANGE",
            "FORMANT_PRESERVE", "VOCODER_ROSENBERG", "VOCODER_CHORD", "NORMAL_STRETCH", "ROBOTIC", "WHISPER", "NORMAL_PV",
            "PHASE_LOCKED", "INT_RATIO"]

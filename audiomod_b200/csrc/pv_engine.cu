@@ -562,15 +562,15 @@ int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_
 }
 
 // One group of rows on one context; everything is enqueued on ctx.st.
-static int batch_run_group(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, const float *d_in, int64_t in_stride, float *d_out, int64_t out_stride,
-                           int row0, int rows) {
+static int batch_run_group(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride,
+                           int row0, int rows, int fmt) {
     Pipeline &pl = b->pl;
     int rc;
     ctx.ws.rows = rows;
     if ((rc = ctx.ws.reset_state(pl, ctx.st))) return rc;
     DevRows g{};
     g.rows = rows; g.channels = b->cfg.channels;
-    g.in = d_in; g.in_stride = in_stride; g.in_base = 0;
+    g.in = d_in; g.in_stride = in_stride; g.in_base = 0; g.fmt = fmt;
     g.n_in = b->d_nin.as<int64_t>() + row0;
     g.n_out = b->d_nout.as<int64_t>() + row0;
     g.out = d_out; g.out_stride = out_stride; g.out_base = 0;
@@ -587,7 +587,8 @@ static int batch_run_group(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, const float *d
 int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt, void *cuda_stream) {
     if (!b || !d_in || !d_out) return fail(PVGPU_EINVAL, "null argument");
     if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
-    if (fmt != PVGPU_F32) return fail(PVGPU_EINVAL, "device runs take float32 rows");
+    if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
+    const size_t esz = fmt == PVGPU_S16 ? sizeof(short) : sizeof(float);
     CU(cudaSetDevice(b->pl.device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
     const int total_rows = b->n_streams * b->cfg.channels;
@@ -604,8 +605,8 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
     for (int i = 0; i < n_ctx; ++i) CU(cudaStreamWaitEvent(b->ctx[i].st, b->ev_fork, 0));
     for (int gi = 0; gi < n_groups; ++gi) {
         const int row0 = gi * group, rows = std::min(group, total_rows - row0);
-        if ((rc = batch_run_group(b, b->ctx[gi % n_ctx], (const float *)d_in + (int64_t)row0 * in_stride, in_stride,
-                                  (float *)d_out + (int64_t)row0 * out_stride, out_stride, row0, rows))) return rc;
+        if ((rc = batch_run_group(b, b->ctx[gi % n_ctx], (const char *)d_in + (int64_t)row0 * in_stride * esz, in_stride,
+                                  (char *)d_out + (int64_t)row0 * out_stride * esz, out_stride, row0, rows, fmt))) return rc;
     }
     // join
     for (int i = 0; i < n_ctx; ++i) {
@@ -619,7 +620,7 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
 // rows [r0, r0+rows) between host row pointers and a dense device block; one 2-D copy when the host rows are evenly
 // spaced, one copy per row otherwise
 static int copy_rows(void *dev, int64_t dev_stride, const void *const *host_rows, int r0, int rows, const int64_t *lens, int C, bool to_device,
-                     cudaStream_t st, int64_t *bytes) {
+                     size_t esz, cudaStream_t st, int64_t *bytes) {
     bool regular = rows > 1;
     const ptrdiff_t pitch = rows > 1 ? (const char *)host_rows[r0 + 1] - (const char *)host_rows[r0] : 0;
     int64_t maxlen = 0;
@@ -627,19 +628,19 @@ static int copy_rows(void *dev, int64_t dev_stride, const void *const *host_rows
         maxlen = std::max(maxlen, lens[(r0 + r) / C]);
         if (r + 1 < rows && (const char *)host_rows[r0 + r + 1] - (const char *)host_rows[r0 + r] != pitch) regular = false;
     }
-    if (regular && pitch >= (ptrdiff_t)(maxlen * sizeof(float)) && maxlen > 0) {
-        if (to_device) CU(cudaMemcpy2DAsync(dev, dev_stride * sizeof(float), host_rows[r0], (size_t)pitch, maxlen * sizeof(float), rows, cudaMemcpyHostToDevice, st));
-        else CU(cudaMemcpy2DAsync((void *)host_rows[r0], (size_t)pitch, dev, dev_stride * sizeof(float), maxlen * sizeof(float), rows, cudaMemcpyDeviceToHost, st));
-        for (int r = 0; r < rows; ++r) *bytes += sizeof(float) * lens[(r0 + r) / C];
+    if (regular && pitch >= (ptrdiff_t)(maxlen * esz) && maxlen > 0) {
+        if (to_device) CU(cudaMemcpy2DAsync(dev, dev_stride * esz, host_rows[r0], (size_t)pitch, maxlen * esz, rows, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpy2DAsync((void *)host_rows[r0], (size_t)pitch, dev, dev_stride * esz, maxlen * esz, rows, cudaMemcpyDeviceToHost, st));
+        for (int r = 0; r < rows; ++r) *bytes += esz * lens[(r0 + r) / C];
         return PVGPU_OK;
     }
     for (int r = 0; r < rows; ++r) {
         const int64_t n = lens[(r0 + r) / C];
         if (!n) continue;
-        float *d = (float *)dev + (int64_t)r * dev_stride;
-        if (to_device) CU(cudaMemcpyAsync(d, host_rows[r0 + r], sizeof(float) * n, cudaMemcpyHostToDevice, st));
-        else CU(cudaMemcpyAsync((void *)host_rows[r0 + r], d, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-        *bytes += sizeof(float) * n;
+        char *d = (char *)dev + (int64_t)r * dev_stride * esz;
+        if (to_device) CU(cudaMemcpyAsync(d, host_rows[r0 + r], esz * n, cudaMemcpyHostToDevice, st));
+        else CU(cudaMemcpyAsync((void *)host_rows[r0 + r], d, esz * n, cudaMemcpyDeviceToHost, st));
+        *bytes += esz * n;
     }
     return PVGPU_OK;
 }
@@ -647,7 +648,8 @@ static int copy_rows(void *dev, int64_t dev_stride, const void *const *host_rows
 int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt) {
     if (!b || !in_rows || !out_rows) return fail(PVGPU_EINVAL, "null argument");
     if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
-    if (fmt != PVGPU_F32) return fail(PVGPU_EINVAL, "only float32 rows are supported");
+    if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
+    const size_t esz = fmt == PVGPU_S16 ? sizeof(short) : sizeof(float);
     CU(cudaSetDevice(b->pl.device));
     const int C = b->cfg.channels;
     const int total_rows = b->n_streams * C;
@@ -662,8 +664,8 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
     for (int i = 0; i < n_ctx; ++i) {
         pvgpu_batch::Ctx &c = b->ctx[i];
         if ((rc = c.ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
-        CU(c.stage_in.ensure(sizeof(float) * (size_t)group * in_stride));
-        CU(c.stage_out.ensure(sizeof(float) * (size_t)group * out_stride));
+        CU(c.stage_in.ensure(esz * (size_t)group * in_stride));
+        CU(c.stage_out.ensure(esz * (size_t)group * out_stride));
     }
     if ((rc = b->prepare_runs())) return rc;
     b->pl.launches = 0;
@@ -673,9 +675,9 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
     for (int gi = 0; gi < n_groups; ++gi) {
         pvgpu_batch::Ctx &c = b->ctx[gi % n_ctx];
         const int row0 = gi * group, rows = std::min(group, total_rows - row0);
-        if ((rc = copy_rows(c.stage_in.p, in_stride, in_rows, row0, rows, b->n_in.data(), C, true, c.st, &b->h2d))) return rc;
-        if ((rc = batch_run_group(b, c, c.stage_in.as<float>(), in_stride, c.stage_out.as<float>(), out_stride, row0, rows))) return rc;
-        if ((rc = copy_rows(c.stage_out.p, out_stride, (const void *const *)out_rows, row0, rows, b->n_out.data(), C, false, c.st, &b->d2h))) return rc;
+        if ((rc = copy_rows(c.stage_in.p, in_stride, in_rows, row0, rows, b->n_in.data(), C, true, esz, c.st, &b->h2d))) return rc;
+        if ((rc = batch_run_group(b, c, c.stage_in.p, in_stride, c.stage_out.p, out_stride, row0, rows, fmt))) return rc;
+        if ((rc = copy_rows(c.stage_out.p, out_stride, (const void *const *)out_rows, row0, rows, b->n_out.data(), C, false, esz, c.st, &b->d2h))) return rc;
     }
     for (int i = 0; i < n_ctx; ++i) CU(cudaStreamSynchronize(b->ctx[i].st));
     return PVGPU_OK;

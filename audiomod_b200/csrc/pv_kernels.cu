@@ -26,6 +26,22 @@ __device__ __noinline__ float pv_atan2f_rare(float y, float x) { return pv_atan2
 
 namespace pvgpu {
 
+// PCM sample formats at the batch boundary.  int16 follows the reference's WAV reader / writer: in = (float)(s * (1.0/32768))
+// (main/wavfile.cc:733-752, exact in float), out = (short)(int)clamp(x * 32768.f, -32768, 32767), truncating toward zero
+// (wavfile.cc:1294-1306, 1508-1526).
+__device__ __forceinline__ float pcm_load(const void *base, int fmt, int64_t idx) {
+    return fmt ? (float)((const short *)base)[idx] * (1.0f / 32768.0f) : ((const float *)base)[idx];
+}
+__device__ __forceinline__ void pcm_store(void *base, int fmt, int64_t idx, float v) {
+    if (fmt) {
+        float s = __fmul_rn(v, 32768.0f);
+        s = s > 32767.0f ? 32767.0f : (s < -32768.0f ? -32768.0f : s);
+        ((short *)base)[idx] = (short)(int)s;
+    } else {
+        ((float *)base)[idx] = v;
+    }
+}
+
 // All butterfly stages of the nc-point complex FFT, in place in shared memory (data already permuted).
 template <bool kInverse>
 __device__ __forceinline__ void fft_stages(const DevPlan &p, float2 *F) {
@@ -66,12 +82,12 @@ __global__ void k_analyse(const DevPlan p, const DevRows g, long k0) {
     const int row = blockIdx.y;
     const long k = k0 + blockIdx.x;
     const int N = p.N, nc = p.nc, hs = N / 2;
-    const float *__restrict__ x = g.in + (int64_t)row * g.in_stride;
+    const int64_t xoff = (int64_t)row * g.in_stride - g.in_base;
     const int64_t start = (int64_t)k * p.hop;
     const int64_t nvalid = g.n_in[row];
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
         const int64_t gi = start + j;
-        const float v = gi < nvalid ? x[gi - g.in_base] : 0.f;
+        const float v = gi < nvalid ? pcm_load(g.in, g.fmt, xoff + gi) : 0.f;
         s_t[(j + hs) & (N - 1)] = __fmul_rn(v, __ldg(&p.window[j]));
     }
     __syncthreads();
@@ -127,7 +143,7 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
     if (active) {
         const long k = k0 + f;
         const int64_t start = (int64_t)k * p.hop;
-        const float *__restrict__ x = g.in + (int64_t)row * g.in_stride + (start - g.in_base);
+        const int64_t xoff = (int64_t)row * g.in_stride + (start - g.in_base);
         const int64_t left = g.n_in[row] - start;
         const int valid = left < 0 ? 0 : (left > N ? N : (int)left);   // samples of this frame that exist; the rest are zeros
         const float2 *__restrict__ w2 = (const float2 *)p.window;
@@ -140,8 +156,8 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int s0 = 2 * (t + T * i);
-            x0[i] = s0 < valid ? x[s0] : 0.f;
-            x1[i] = s0 + 1 < valid ? x[s0 + 1] : 0.f;
+            x0[i] = s0 < valid ? pcm_load(g.in, g.fmt, xoff + s0) : 0.f;
+            x1[i] = s0 + 1 < valid ? pcm_load(g.in, g.fmt, xoff + s0 + 1) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -904,7 +920,7 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
                 s_in[e] = v;
             } else if (sl >= first_run_slice && i < T.n_store[sl]) {
                 // no resampling: the normalised sample is the output sample (n_write / n_out clip)
-                g.out[row_out + out_first + T.out_rel[sl] + i] = v;
+                pcm_store(g.out, g.fmt, row_out + out_first + T.out_rel[sl] + i, v);
             }
         }
     }
@@ -920,7 +936,7 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
     constexpr int nb = OV > 0 ? OV : 1;
     const unsigned *__restrict__ ent_tab = rs_ent + hdr.ent_off;
     const float *__restrict__ frac_tab = rs_frac + hdr.ent_off;
-    float *__restrict__ orow = g.out + row_out + hdr.out_first;
+    const int64_t orow = row_out + hdr.out_first;
     const int64_t out_limit = g.n_out[row] - hdr.out_first;
     const int in_shift = (int)(hdr.u_lo - u_lo) - kResPad;   // hdr.u_lo == u_lo; entries are biased by kResPad
     (void)out_first;
@@ -948,7 +964,7 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
                 float sum = 0.f;
                 const float *__restrict__ tt = p.rs_table + (size_t)__float_as_uint(__ldg(&frac_tab[blk + lane + 32 * u])) * L;
                 for (int j = 0; j < L; ++j) sum += xs[u][j] * __ldg(&tt[j]);
-                orow[ent[u] & 0xffffu] = sum;
+                pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), sum);
             }
         } else {
             const float4 *q = s_quad + 4 + OV - bucket;
@@ -978,7 +994,7 @@ __global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const Dev
                 const float i1 = frac + 0.5f * frac * frac - 0.5f * frac * frac * frac;
                 const float i3 = -0.33333f * frac + 0.5f * frac * frac - 0.16667f * frac * frac * frac;
                 const float i2 = (float)(1. - i0 - i1 - i3);
-                orow[ent[u] & 0xffffu] = (i0 * acc[u][0]) + (i1 * acc[u][1]) + (i2 * acc[u][2]) + (i3 * acc[u][3]);
+                pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), (i0 * acc[u][0]) + (i1 * acc[u][1]) + (i2 * acc[u][2]) + (i3 * acc[u][3]));
             }
         }
     }

@@ -36,14 +36,15 @@ struct DevPlan {
 struct DevRows {
     int rows;                 // channel rows in this group (streams * channels)
     int channels;
-    const float *in;          // [rows][in_stride], element 0 is input sample in_base
+    const void *in;           // [rows][in_stride] float32 or int16 PCM (fmt), element 0 is input sample in_base
+    int fmt;                  // 0: float32 rows, 1: int16 rows (input and output)
     int64_t in_stride, in_base;
     const int64_t *n_in;      // per row: valid input samples (zeros beyond), global coordinates
     float *mag, *phase;       // [rows][F][Hp] spectra of the current frame chunk
     int F;                    // frame slots per row in mag/phase
     float *frames;            // [rows][Fr][N] synthesised frames, slot = frame % Fr
     int Fr;
-    float *out;               // [rows][out_stride], element 0 is output position out_base
+    void *out;                // [rows][out_stride] (fmt), element 0 is output position out_base
     int64_t out_stride, out_base;
     const int64_t *n_out;     // per row: output positions >= n_out are not stored (truncation to the stream's length)
     float *prev_phase, *prev_out;   // [rows][half] phase-core state

@@ -162,15 +162,17 @@ class PhaseVocoderBatch:
             op[r] = out_rows[r] if isinstance(out_rows[r], int) else out_rows[r].ctypes.data
         check(_lib.lib().pvgpu_batch_run_host(self._h, ip, op, fmt))
 
-    def run(self, streams):
-        """streams: list of float32 arrays [channels, n_i].  Plans for these lengths and returns the outputs."""
-        xs = [np.ascontiguousarray(x, dtype=np.float32) for x in streams]
+    def run(self, streams, fmt=_lib.F32):
+        """streams: list of arrays [channels, n_i], float32 (fmt F32) or int16 PCM (fmt S16; converted on the device the
+        way the reference's WAV reader / writer does).  Plans for these lengths and returns the outputs in the same format."""
+        dt = np.int16 if fmt == _lib.S16 else np.float32
+        xs = [np.ascontiguousarray(x, dtype=dt) for x in streams]
         assert len(xs) == self.n_streams and all(x.shape[0] == self.channels for x in xs)
         n_out = self.plan([x.shape[1] for x in xs])
-        outs = [np.zeros((self.channels, int(n_out[s])), dtype=np.float32) for s in range(self.n_streams)]
+        outs = [np.zeros((self.channels, int(n_out[s])), dtype=dt) for s in range(self.n_streams)]
         in_rows = [xs[s][c] for s in range(self.n_streams) for c in range(self.channels)]
         out_rows = [outs[s][c] for s in range(self.n_streams) for c in range(self.channels)]
-        self.run_host_rows(in_rows, out_rows)
+        self.run_host_rows(in_rows, out_rows, fmt)
         return outs
 
     KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "ola_resample", "unused", "fixed_phase")

@@ -36,7 +36,7 @@ UNIT = "audio-s/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
     ap.add_argument("--secs", type=float, default=10.0)
@@ -125,33 +125,57 @@ def reference_arm(args):
 
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML; nvidia-smi as a fallback)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.sm, self.max_sm, self.reasons, self.stop_flag = index, [], [], set(), threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        self.max_sm.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [v.strip() for v in out.split(",")]
+        self.sm.append(float(c[0]))
+        self.max_sm.append(float(c[1]))
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02 if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.max_sm) if self.max_sm else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def make_inputs(torch, dev, streams, n, seed):
@@ -310,6 +334,26 @@ def main():
         e2e = {"value": audio_sec_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] * world,
                "d2h_bytes_per_step": st["d2h_bytes"] * world, "ms_per_step": dt * 1e3, "format": "f32 in, f32 out, pinned host memory",
                "result_checksum": float(h_out[:, :int(n_out.min())].double().abs().mean().item())}
+
+        # the same through int16 PCM rows (the reference CLI's own I/O format: 16-bit WAV in, 16-bit WAV out), reported beside it
+        del h_in, h_out
+        q_in = torch.empty((S, stride), dtype=torch.int16, pin_memory=True)
+        q_in.copy_(torch.round(d_in * 32768.0).clamp_(-32768, 32767).to(torch.int16))
+        q_out = torch.empty((S, out_stride), dtype=torch.int16, pin_memory=True)
+        qi = [q_in.data_ptr() + 2 * stride * r for r in range(S)]
+        qo = [q_out.data_ptr() + 2 * out_stride * r for r in range(S)]
+        batch.run_host_rows(qi, qo, A.S16)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            batch.run_host_rows(qi, qo, A.S16)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0) / args.steps
+        st = batch.stats()
+        e2e["s16"] = {"value": audio_sec_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] * world,
+                      "d2h_bytes_per_step": st["d2h_bytes"] * world, "ms_per_step": dt * 1e3,
+                      "format": "int16 PCM in, int16 PCM out, pinned host memory"}
+        del q_in, q_out
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -189,6 +189,26 @@ def test_stereo_identical_channels_quirk(A, oracle):
     assert not np.array_equal(rs[0], rs[1])
 
 
+def test_int16_pcm_rows(A, oracle):
+    """int16 PCM in and out (the reference CLI's WAV format): device-side conversions follow main/wavfile.cc:733-752 and
+    :1294-1306,1508-1526 (x * 32768, clamp, truncate toward zero).  A 1e-7 float difference can flip the truncation by 1 LSB."""
+    from audiomod_b200.synth import synth_int16
+    sr = 44100
+    for ch, kw in ((1, dict(semitones=7.0)), (2, dict(timeratio=1.5, mode=5, fftsize=4096))):
+        pcm = [synth_int16(900 + i, sr, 0.5 - 0.1 * i, ch) for i in range(3)]
+        b = A.PhaseVocoderBatch(3, pcm[0].shape[1], sr, ch, kw.get("timeratio", 1.0), kw.get("semitones", 0.0), kw.get("mode", 0), 1,
+                                kw.get("fftsize", 2048))
+        ys = b.run(pcm, fmt=A.S16)
+        b.close()
+        for x, y in zip(pcm, ys):
+            xf = (x.astype(np.float64) * (1.0 / 32768.0)).astype(np.float32)
+            r = oracle.run_offline(xf, sr, **kw)
+            want = np.clip(r * np.float32(32768.0), -32768.0, 32767.0).astype(np.int32)   # astype truncates toward zero
+            assert y.dtype == np.int16 and y.shape == want.shape
+            d = np.abs(y.astype(np.int32) - want)
+            assert d.max() <= 1 and (d == 0).mean() > 0.995
+
+
 def test_device_resident_entry_point(A, oracle):
     """pvgpu_batch_run_device with caller-owned device buffers (torch tensors) on torch's current stream."""
     torch = pytest.importorskip("torch")
