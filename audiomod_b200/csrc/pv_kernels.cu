@@ -128,7 +128,7 @@ __global__ void k_analyse(const DevPlan p, const DevRows g, long k0) {
 // k_analyse_t<N>: register-tiled version for N = 512..8192 (pv_fft.cuh).  T = N/32 threads own a frame; a CTA of
 // max(T, 256) threads handles 256/T consecutive frames of the chunk.
 // ------------------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool kS16>
 __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(const DevPlan p, const DevRows g, long k0, int nf, int total) {
     constexpr int NC = N / 2;
     using S = FftShape<NC>;
@@ -153,11 +153,32 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
         // every store is base + compile-time constant.
         const int base = fft_pad(fft_slot_of_input<NC>(t));
         float x0[16], x1[16];
+        if (kS16) {
+            const short *__restrict__ xp = (const short *)g.in + xoff + 2 * t;
+            if (valid == N) {   // whole frame inside the stream: no per-sample bounds
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int s0 = 2 * (t + T * i);
-            x0[i] = s0 < valid ? pcm_load(g.in, g.fmt, xoff + s0) : 0.f;
-            x1[i] = s0 + 1 < valid ? pcm_load(g.in, g.fmt, xoff + s0 + 1) : 0.f;
+                for (int i = 0; i < 16; ++i) { x0[i] = (float)xp[2 * T * i] * (1.0f / 32768.0f); x1[i] = (float)xp[2 * T * i + 1] * (1.0f / 32768.0f); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int s0 = 2 * (t + T * i);
+                    x0[i] = s0 < valid ? (float)xp[2 * T * i] * (1.0f / 32768.0f) : 0.f;
+                    x1[i] = s0 + 1 < valid ? (float)xp[2 * T * i + 1] * (1.0f / 32768.0f) : 0.f;
+                }
+            }
+        } else {
+            const float *__restrict__ xp = (const float *)g.in + xoff + 2 * t;
+            if (valid == N) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { x0[i] = xp[2 * T * i]; x1[i] = xp[2 * T * i + 1]; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int s0 = 2 * (t + T * i);
+                    x0[i] = s0 < valid ? xp[2 * T * i] : 0.f;
+                    x1[i] = s0 + 1 < valid ? xp[2 * T * i + 1] : 0.f;
+                }
+            }
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -1037,7 +1058,8 @@ template <int N> static void launch_analyse_t(const DevPlan &p, const DevRows &g
     using S = FftShape<N / 2>;
     constexpr int T = S::kThreads, G = (T >= 256) ? 1 : 256 / T;
     const int total = nframes * g.rows;
-    k_analyse_t<N><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, k0, nframes, total);
+    if (g.fmt) k_analyse_t<N, true><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, k0, nframes, total);
+    else k_analyse_t<N, false><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, k0, nframes, total);
 }
 
 void launch_analyse(const DevPlan &p, const DevRows &g, long k0, int nframes, cudaStream_t st) {

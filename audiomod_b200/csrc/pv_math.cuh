@@ -149,26 +149,17 @@ PV_HD float pv_atan2f_fast(float y, float x) {
     const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
     const int k = (iy - ix) >> 23;
     // iy-1 / ix-1 as unsigned: rejects zero and inf/NaN with one compare each
-    const bool common = ((uint32_t)(iy - 1) < 0x7f7fffffu) & ((uint32_t)(ix - 1) < 0x7f7fffffu) & (hx != 0x3f800000) & (k <= 60) & (k >= -60);
-#if defined(__CUDA_ARCH__)
-#define PV_ATAN2_RARE pv_atan2f_rare
-#else
-#define PV_ATAN2_RARE pv_atan2f
-#endif
-    if (!common) return PV_ATAN2_RARE(y, x);
-    const float q = PV_I2F(PV_F2I(PV_DIV(y, x)) & 0x7fffffff);  // fabsf(y/x)
+    bool common = ((uint32_t)(iy - 1) < 0x7f7fffffu) & ((uint32_t)(ix - 1) < 0x7f7fffffu) & (hx != 0x3f800000) & (k <= 60) & (k >= -60);
+    const float q = PV_I2F(PV_F2I(PV_DIV(y, x)) & 0x7fffffff);  // fabsf(y/x); harmless when the arguments are not "common"
     const int32_t iq = PV_F2I(q);
-    if (iq >= 0x4c000000) return PV_ATAN2_RARE(y, x);            // |y/x| >= 2^25 (or the quotient overflowed)
-    float a, b, c, d, hi, lo;
-    if (iq < 0x3f300000) {          // < 11/16   (also covers < 7/16, where these are unused)
-        a = 2.0f; b = -1.0f; c = 1.0f; d = 2.0f; hi = PV_I2F(0x3eed6338); lo = PV_I2F(0x31ac3769);
-    } else if (iq < 0x3f980000) {   // < 19/16
-        a = 1.0f; b = -1.0f; c = 1.0f; d = 1.0f; hi = PV_I2F(0x3f490fda); lo = PV_I2F(0x33222168);
-    } else if (iq < 0x401c0000) {   // < 39/16
-        a = 1.0f; b = -1.5f; c = 1.5f; d = 1.0f; hi = PV_I2F(0x3f7b985e); lo = PV_I2F(0x33140fb4);
-    } else {
-        a = 0.0f; b = -1.0f; c = 1.0f; d = 0.0f; hi = PV_I2F(0x3fc90fda); lo = PV_I2F(0x33a22168);
-    }
+    common &= iq < 0x4c000000;                                  // |y/x| >= 2^25 (or the quotient overflowed) goes the long way
+    const bool r1 = iq >= 0x3f300000, r2 = iq >= 0x3f980000, r3 = iq >= 0x401c0000;   // 11/16, 19/16, 39/16
+    const float a = r3 ? 0.0f : (r1 ? 1.0f : 2.0f);
+    const float b = r2 && !r3 ? -1.5f : -1.0f;
+    const float c = r2 && !r3 ? 1.5f : 1.0f;
+    const float d = r3 ? 0.0f : (r1 ? 1.0f : 2.0f);
+    const float hi = PV_I2F(r3 ? 0x3fc90fda : (r2 ? 0x3f7b985e : (r1 ? 0x3f490fda : 0x3eed6338)));
+    const float lo = PV_I2F(r3 ? 0x33a22168 : (r2 ? 0x33140fb4 : (r1 ? 0x33222168 : 0x31ac3769)));
     const bool small = iq < 0x3ee00000;  // < 7/16: no reduction
     const float red = PV_DIV(PV_ADD(PV_MUL(a, q), b), PV_ADD(PV_MUL(c, q), d));
     const float t = small ? q : red;
@@ -180,17 +171,17 @@ PV_HD float pv_atan2f_fast(float y, float x) {
     const float s1 = PV_MUL(z, PV_ADD(a0, PV_MUL(w, PV_ADD(a2, PV_MUL(w, PV_ADD(a4, PV_MUL(w, PV_ADD(a6, PV_MUL(w, PV_ADD(a8, PV_MUL(w, a10)))))))))));
     const float s2 = PV_MUL(w, PV_ADD(a1, PV_MUL(w, PV_ADD(a3, PV_MUL(w, PV_ADD(a5, PV_MUL(w, PV_ADD(a7, PV_MUL(w, a9)))))))));
     const float ts = PV_MUL(t, PV_ADD(s1, s2));
-    float zr;
-    if (small) {
-        // |t| < 2^-29 returns t unchanged in the reference; t - t*(s1+s2) rounds to t there as well, except that the
-        // reference skips the arithmetic -- identical values for every non-zero t (t is non-zero here)
-        zr = iq < 0x31000000 ? t : PV_SUB(t, ts);
-    } else {
-        zr = PV_SUB(hi, PV_SUB(PV_SUB(ts, lo), t));
-    }
+    // |t| < 2^-29 returns t unchanged in the reference; t - t*(s1+s2) rounds to t there as well (t is non-zero here)
+    const float zs = iq < 0x31000000 ? t : PV_SUB(t, ts);
+    const float zb = PV_SUB(hi, PV_SUB(PV_SUB(ts, lo), t));
+    const float zr = small ? zs : zb;
     const float pi = PV_I2F(0x40490fdb), pi_lo = PV_I2F(0xb3bbbd2e);
-    // the (hx < 0 && k < -60) shortcut of the reference is excluded by `common`
-    if (hx >= 0) return hy < 0 ? -zr : zr;
-    const float zl = PV_SUB(zr, pi_lo);
-    return hy < 0 ? PV_SUB(zl, pi) : PV_SUB(pi, zl);
+    // quadrant: x > 0: +-zr;  x < 0: +-(pi - (zr - pi_lo))   [(zr - pi_lo) - pi == -(pi - (zr - pi_lo)) exactly]
+    const float v = hx >= 0 ? zr : PV_SUB(pi, PV_SUB(zr, pi_lo));
+    const float res = PV_I2F(PV_F2I(v) ^ (hy & (int32_t)0x80000000));
+#if defined(__CUDA_ARCH__)
+    return common ? res : pv_atan2f_rare(y, x);
+#else
+    return common ? res : pv_atan2f(y, x);
+#endif
 }
