@@ -463,9 +463,14 @@ __global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const Dev
 
     const int total = nframes * C;
     float mg[E], phv[E];
-    auto fetch = [&](int it) {
-        const int f = it / C, c = it - f * C;
-        const int64_t base = (((int64_t)stream * C + c) * g.F + f) * p.Hp + b0;
+    // element offset of (frame f, channel c, bin b0) in the spectra: advanced incrementally, one (frame, channel) per step
+    const int64_t ch_step = (int64_t)g.F * p.Hp;            // next channel, same frame
+    const int64_t fr_step = (int64_t)p.Hp - (C - 1) * ch_step;   // channel C-1 of frame f -> channel 0 of frame f+1
+    int64_t off_fetch = (int64_t)stream * C * ch_step + b0;
+    int c_fetch = 0;
+    auto fetch = [&]() {
+        const int64_t base = off_fetch;
+        if (++c_fetch == C) { c_fetch = 0; off_fetch += fr_step; } else off_fetch += ch_step;
 #pragma unroll
         for (int e = 0; e < E; e += 4) {
             const float4 m4 = *(const float4 *)(g.mag + base + e);
@@ -474,13 +479,15 @@ __global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const Dev
             phv[e] = p4.x; phv[e + 1] = p4.y; phv[e + 2] = p4.z; phv[e + 3] = p4.w;
         }
     };
-    if (total > 0) fetch(0);
+    if (total > 0) fetch();
+    int64_t off_cur = (int64_t)stream * C * ch_step + b0;
+    int f = 0, c = 0;
     const float hopf = (float)p.hop;
     __syncthreads();
 
+    const SliceRec *__restrict__ rec_f = recs + (k0 - recs_base);
     for (int it = 0; it < total; ++it) {
-        const int f = it / C, c = it - f * C;
-        const float phase_inc = (float)recs[k0 + f - recs_base].phase_inc;
+        const float phase_inc = (float)rec_f[f].phase_inc;
         float *pp = s_pp + c * half, *po = s_po + c * half;
         float ph[E], m[E];
 #pragma unroll
@@ -513,7 +520,7 @@ __global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const Dev
             if (lane >= d) incl += v;
         }
         if (lane == 31) s_wsum[warp] = incl;
-        if (it + 1 < total) fetch(it + 1);   // prefetch the next (frame, channel) while this one is processed
+        if (it + 1 < total) fetch();   // prefetch the next (frame, channel) while this one is processed
         __syncthreads();   // (B)
         int base = 0, npk = 0;
         for (int wv = 0; wv < nwarp; ++wv) { const int v = s_wsum[wv]; npk += v; if (wv < warp) base += v; }
@@ -523,7 +530,7 @@ __global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const Dev
 #pragma unroll
             for (int e = 0; e < E; ++e) if (flags & (1u << e)) s_cur[r++] = b0 + e;
         }
-        float *__restrict__ gph = g.phase + (((int64_t)stream * C + c) * g.F + f) * p.Hp + b0;
+        float *__restrict__ gph = g.phase + off_cur;
         if (first) {
             // first call of the process: pass the analysis phase through and seed the state (:606-616)
 #pragma unroll
@@ -588,6 +595,7 @@ __global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const Dev
         { int *tsw = s_prev; s_prev = s_cur; s_cur = tsw; }
         nprev = npk;
         first = false;
+        if (++c == C) { c = 0; ++f; off_cur += fr_step; } else off_cur += ch_step;
         (void)kMaxOwn;
     }
     __syncthreads();
@@ -782,13 +790,20 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
         const int sa = fft_pad(fft_slot_of_input<NC>(t)), sb = fft_pad(fft_slot_of_input<NC>((T - t) & (T - 1)));
         // rolled in groups of two pairs: four independent loads in flight per step without unrolling the (large) sincos
         // expansion 16 times, which would not fit the instruction cache
+        float2 lo[2], hi[2], nlo[2], nhi[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            lo[u] = bin.load(t + T * u);
+            hi[u] = bin.load(NC - (t + T * u));
+        }
 #pragma unroll 1
         for (int q0 = 0; q0 < Q; q0 += 2) {
-            float2 lo[2], hi[2];
+            if (q0 + 2 < Q) {   // the next group's loads are in flight while this group's sincos run
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                lo[u] = bin.load(t + T * (q0 + u));
-                hi[u] = bin.load(NC - (t + T * (q0 + u)));
+                for (int u = 0; u < 2; ++u) {
+                    nlo[u] = bin.load(t + T * (q0 + 2 + u));
+                    nhi[u] = bin.load(NC - (t + T * (q0 + 2 + u)));
+                }
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -809,6 +824,8 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
                         make_float2(b.x, -b.y);
                 }
             }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { lo[u] = nlo[u]; hi[u] = nhi[u]; }
         }
         if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)
             const float2 fk = bin(NC / 2);
