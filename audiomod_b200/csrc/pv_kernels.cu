@@ -790,20 +790,13 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
         const int sa = fft_pad(fft_slot_of_input<NC>(t)), sb = fft_pad(fft_slot_of_input<NC>((T - t) & (T - 1)));
         // rolled in groups of two pairs: four independent loads in flight per step without unrolling the (large) sincos
         // expansion 16 times, which would not fit the instruction cache
-        float2 lo[2], hi[2], nlo[2], nhi[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            lo[u] = bin.load(t + T * u);
-            hi[u] = bin.load(NC - (t + T * u));
-        }
 #pragma unroll 1
         for (int q0 = 0; q0 < Q; q0 += 2) {
-            if (q0 + 2 < Q) {   // the next group's loads are in flight while this group's sincos run
+            float2 lo[2], hi[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    nlo[u] = bin.load(t + T * (q0 + 2 + u));
-                    nhi[u] = bin.load(NC - (t + T * (q0 + 2 + u)));
-                }
+            for (int u = 0; u < 2; ++u) {
+                lo[u] = bin.load(t + T * (q0 + u));
+                hi[u] = bin.load(NC - (t + T * (q0 + u)));
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -824,8 +817,6 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
                         make_float2(b.x, -b.y);
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) { lo[u] = nlo[u]; hi[u] = nhi[u]; }
         }
         if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)
             const float2 fk = bin(NC / 2);
