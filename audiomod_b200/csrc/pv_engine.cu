@@ -402,7 +402,14 @@ struct pvgpu_batch {
     ~pvgpu_batch() {
         for (auto &c : ctx) { if (c.st) cudaStreamDestroy(c.st); if (c.done) cudaEventDestroy(c.done); }
         if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto e : ev_pool) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+    }
+    std::vector<cudaEvent_t> ev_pool;   // chunk events of the time-sliced host pipeline
+    bool time_sliced = true;
+    size_t max_ws_bytes = (size_t)24 << 30;   // largest workspace a single group may take
+    size_t ws_bytes_per_row() const {
+        return sizeof(float) * ((size_t)2 * frames_per_chunk * pl.p.Hp + (size_t)(frames_per_chunk + halo) * pl.p.N + 2 * (size_t)pl.p.half);
     }
     int run_for_chunk = 0;   // frames_per_chunk the resampler work lists were built for
     int prepare_runs() {
@@ -416,7 +423,8 @@ struct pvgpu_batch {
     }
     int group_rows() const {
         const int C = cfg.channels, total = n_streams * C;
-        int group = rows_per_group > 0 ? rows_per_group : 512;
+        int group = rows_per_group;
+        if (group <= 0) group = (size_t)total * ws_bytes_per_row() <= max_ws_bytes ? total : 1024;   // widest launches that fit
         group = std::max(C, (group / C) * C);
         return std::min(group, total);
     }
@@ -488,7 +496,7 @@ int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info) {
 int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, int contexts) {
     if (!b) return fail(PVGPU_EINVAL, "null batch");
     if (frames_per_chunk > 0) b->frames_per_chunk = frames_per_chunk;
-    if (rows_per_group > 0) b->rows_per_group = rows_per_group;
+    if (rows_per_group > 0) { b->rows_per_group = rows_per_group; b->time_sliced = false; }   // explicit row groups pipeline across rows instead of time
     if (contexts > 0) b->n_contexts = std::min(contexts, (int)pvgpu_batch::kCtx);
     return PVGPU_OK;
 }
@@ -645,6 +653,77 @@ static int copy_rows(void *dev, int64_t dev_stride, const void *const *host_rows
     return PVGPU_OK;
 }
 
+// byte distance between consecutive host rows if it is the same for all of them (0 for a single row), else -1
+static ptrdiff_t regular_pitch(const void *const *rows, int n) {
+    if (n < 2) return 0;
+    const ptrdiff_t pitch = (const char *)rows[1] - (const char *)rows[0];
+    for (int r = 1; r + 1 < n; ++r)
+        if ((const char *)rows[r + 1] - (const char *)rows[r] != pitch) return -1;
+    return pitch;
+}
+
+// Host buffers, equal-length streams in evenly spaced host rows: the whole batch is one group (widest launches) and the
+// pipeline runs along TIME instead -- frame chunk c only needs the input columns up to its last frame and completes the
+// output columns of its slices, so H2D of later columns, the kernels of chunk c and D2H of earlier columns overlap on
+// three streams with one 2-D copy per chunk and direction.
+static int run_host_timesliced(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt, size_t esz, int64_t in_stride,
+                               int64_t out_stride, ptrdiff_t in_pitch, ptrdiff_t out_pitch) {
+    Pipeline &pl = b->pl;
+    const int total_rows = b->n_streams * b->cfg.channels;
+    pvgpu_batch::Ctx &c = b->ctx[0];
+    cudaStream_t s_comp = c.st, s_in = b->ctx[1].st, s_out = b->ctx[2].st;
+    int rc;
+    if ((rc = c.ws.ensure(pl, total_rows, b->frames_per_chunk, b->halo))) return rc;
+    CU(c.stage_in.ensure(esz * (size_t)total_rows * in_stride));
+    CU(c.stage_out.ensure(esz * (size_t)total_rows * out_stride));
+    const int F = c.ws.F;
+    const long n_chunks = (b->n_slices + F - 1) / F;
+    while ((long)b->ev_pool.size() < 2 * n_chunks + 2) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        b->ev_pool.push_back(e);
+    }
+    c.ws.rows = total_rows;
+    if ((rc = c.ws.reset_state(pl, s_comp))) return rc;
+    DevRows g{};
+    g.rows = total_rows; g.channels = b->cfg.channels;
+    g.in = c.stage_in.p; g.in_stride = in_stride; g.in_base = 0; g.fmt = fmt;
+    g.n_in = b->d_nin.as<int64_t>(); g.n_out = b->d_nout.as<int64_t>();
+    g.out = c.stage_out.p; g.out_stride = out_stride; g.out_base = 0;
+    c.ws.bind(pl, g);
+    const int64_t n_in = b->n_in[0], n_out = b->n_out[0];
+    int64_t in_done = 0, out_done = 0;
+    const std::vector<SliceRec> &recs = pl.h_recs;
+    for (long ci = 0, k0 = 0; k0 < b->n_slices; ++ci, k0 += F) {
+        const int nf = (int)std::min<long>(F, b->n_slices - k0);
+        const int64_t need = std::min<int64_t>(n_in, (int64_t)(k0 + nf - 1) * pl.p.hop + pl.p.N);
+        if (need > in_done) {
+            CU(cudaMemcpy2DAsync((char *)c.stage_in.p + in_done * esz, in_stride * esz, (const char *)in_rows[0] + in_done * esz, (size_t)in_pitch,
+                                 (size_t)(need - in_done) * esz, total_rows, cudaMemcpyHostToDevice, s_in));
+            b->h2d += (int64_t)(need - in_done) * esz * total_rows;
+            in_done = need;
+        }
+        CU(cudaEventRecord(b->ev_pool[2 * ci], s_in));
+        CU(cudaStreamWaitEvent(s_comp, b->ev_pool[2 * ci], 0));
+        pl.run_frames(g, k0, nf, s_comp);
+        CU(cudaEventRecord(b->ev_pool[2 * ci + 1], s_comp));
+        CU(cudaStreamWaitEvent(s_out, b->ev_pool[2 * ci + 1], 0));
+        const SliceRec &last = recs[k0 + nf - 1 - pl.recs_base];
+        const int64_t avail = std::min<int64_t>(n_out, last.out_off + ((last.flags & 1) ? 0 : last.n_write));
+        if (avail > out_done) {
+            CU(cudaMemcpy2DAsync((char *)out_rows[0] + out_done * esz, (size_t)out_pitch, (const char *)c.stage_out.p + out_done * esz, out_stride * esz,
+                                 (size_t)(avail - out_done) * esz, total_rows, cudaMemcpyDeviceToHost, s_out));
+            b->d2h += (int64_t)(avail - out_done) * esz * total_rows;
+            out_done = avail;
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s_in));
+    CU(cudaStreamSynchronize(s_comp));
+    CU(cudaStreamSynchronize(s_out));
+    return PVGPU_OK;
+}
+
 int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt) {
     if (!b || !in_rows || !out_rows) return fail(PVGPU_EINVAL, "null argument");
     if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
@@ -657,19 +736,27 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
     for (int s = 0; s < b->n_streams; ++s) { in_stride = std::max(in_stride, b->n_in[s]); out_stride = std::max(out_stride, b->n_out[s]); }
     in_stride = std::max<int64_t>((in_stride + 3) & ~(int64_t)3, 4);
     out_stride = std::max<int64_t>((out_stride + 3) & ~(int64_t)3, 4);
+    int rc;
+    if ((rc = b->prepare_runs())) return rc;
+    b->pl.launches = 0;
+    b->h2d = b->d2h = 0;
+    {
+        bool uniform = b->n_slices > 0 && b->n_in[0] > 0 && b->n_out[0] > 0;
+        for (int s = 1; s < b->n_streams && uniform; ++s) uniform = b->n_in[s] == b->n_in[0] && b->n_out[s] == b->n_out[0];
+        const ptrdiff_t ip = regular_pitch(in_rows, total_rows), op = regular_pitch((const void *const *)out_rows, total_rows);
+        const bool fits = (size_t)total_rows * b->ws_bytes_per_row() <= b->max_ws_bytes;
+        if (uniform && fits && b->time_sliced && (total_rows == 1 || (ip >= (ptrdiff_t)(b->n_in[0] * esz) && op >= (ptrdiff_t)(b->n_out[0] * esz))))
+            return run_host_timesliced(b, in_rows, out_rows, fmt, esz, in_stride, out_stride, ip, op);
+    }
     const int group = b->group_rows();
     const int n_groups = (total_rows + group - 1) / group;
     const int n_ctx = std::min(n_groups, b->n_contexts);
-    int rc;
     for (int i = 0; i < n_ctx; ++i) {
         pvgpu_batch::Ctx &c = b->ctx[i];
         if ((rc = c.ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
         CU(c.stage_in.ensure(esz * (size_t)group * in_stride));
         CU(c.stage_out.ensure(esz * (size_t)group * out_stride));
     }
-    if ((rc = b->prepare_runs())) return rc;
-    b->pl.launches = 0;
-    b->h2d = b->d2h = 0;
     // each context's stream carries H2D -> kernels -> D2H of its groups in order; the contexts run concurrently, so the
     // copies of one group overlap the kernels of the others
     for (int gi = 0; gi < n_groups; ++gi) {

@@ -117,8 +117,9 @@ int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);
 enum { PVGPU_KINDS = 8 };
 int pvgpu_batch_profile(pvgpu_batch *b, int enable);
 int pvgpu_batch_kernel_times(pvgpu_batch *b, double *ms /*[PVGPU_KINDS]*/, int64_t *count /*[PVGPU_KINDS]*/);
-/* tuning (0 = keep): frames per chunk, rows per group, and how many groups are in flight at once (1..4; each has its
- * own stream, workspace and staging buffers) */
+/* tuning (0 = keep): frames per chunk; rows per group (by default the whole batch is one group when its workspace fits,
+ * and equal-length batches in evenly spaced host rows are pipelined along time; an explicit value selects pipelining
+ * across row groups); how many row groups are in flight at once (1..4; each has its own stream, workspace and staging) */
 int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, int contexts);
 
 /* ---------------------------------------------------------------------------------------------

@@ -189,6 +189,30 @@ def test_stereo_identical_channels_quirk(A, oracle):
     assert not np.array_equal(rs[0], rs[1])
 
 
+def test_time_sliced_host_pipeline(A, oracle):
+    """Equal-length streams in one contiguous 2-D host array take the time-sliced pipeline (column-block copies overlapping
+    the frame chunks); it must give bit-identical samples to the row-group pipeline and match the oracle."""
+    sr, S, ch = 44100, 6, 2
+    xs = [make_input("x", sr, ch, 0.6, 700 + i) for i in range(S)]
+    n = xs[0].shape[1]
+    X = np.ascontiguousarray(np.concatenate(xs, axis=0))          # [S*ch, n], evenly spaced rows
+    res = {}
+    for name, kw in (("time", dict(frames_per_chunk=16)), ("rows", dict(frames_per_chunk=16, rows_per_group=4))):
+        b = A.PhaseVocoderBatch(S, n, sr, ch, 1.0, 7.0)
+        b.tune(**kw)
+        n_out = b.plan(n)
+        Y = np.full((S * ch, int(n_out[0]) + 5), 9.0, np.float32)  # padded pitch: bytes past n_out must stay untouched
+        b.run_host_rows([X[r] for r in range(S * ch)], [Y[r] for r in range(S * ch)])
+        st = b.stats()
+        b.close()
+        assert np.all(Y[:, int(n_out[0]):] == 9.0)
+        assert st["h2d_bytes"] == X.size * 4 and st["d2h_bytes"] == S * ch * int(n_out[0]) * 4
+        res[name] = Y[:, :int(n_out[0])].copy()
+    assert np.array_equal(res["time"], res["rows"])
+    for i in range(S):
+        assert_parity(res["time"][i * ch:(i + 1) * ch], oracle.run_offline(xs[i], sr, semitones=7.0), f"ts[{i}]")
+
+
 def test_int16_pcm_rows(A, oracle):
     """int16 PCM in and out (the reference CLI's WAV format): device-side conversions follow main/wavfile.cc:733-752 and
     :1294-1306,1508-1526 (x * 32768, clamp, truncate toward zero).  A 1e-7 float difference can flip the truncation by 1 LSB."""
