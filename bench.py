@@ -306,9 +306,15 @@ def main():
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         pass
+    traffic = None
+    try:   # measured DRAM bytes per frame of that kernel from the committed ncu --set full capture, scaled to one launch
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)[dom]["dram_bytes_per_frame"] * slices * S * args.steps / max(dom_launches, 1)
+    except Exception:
+        pass
     kernel_ms_sum = sum(v[0] for v in ktimes.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_total / max(dom_launches, 1),
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_total / max(dom_launches, 1),
                 "avg_launch_ms": dom_ms / max(dom_launches, 1),
                 "kernel_share_of_step": dom_ms / max(kernel_ms_sum, 1e-9),
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
