@@ -137,6 +137,25 @@ template <int T> __device__ __forceinline__ void frame_sync(int group) {
     }
 }
 
+// fft_pad is additive over operands with disjoint bits ((a + b) >> s == (a >> s) + (b >> s) when a + b has no carries), and
+// every access pattern below is "thread part + compile-time part" with disjoint bits, so each shared-memory access is one
+// per-thread base plus an immediate offset.
+
+// natural-order index of v[i] after fft_frame, split into its thread part and its compile-time part
+template <int NC> __device__ __forceinline__ int fft_out_base(int t) {
+    using S = FftShape<NC>;
+    constexpr int M = (NC == 256) ? S::kMid : S::kLast;
+    if (NC == 256 || S::kThirdIsPair) return (t / M) * (16 * M) + (t & (M - 1));
+    return t;
+}
+template <int NC> __device__ __forceinline__ constexpr int fft_out_const(int i) {
+    using S = FftShape<NC>;
+    constexpr int M = (NC == 256) ? S::kMid : S::kLast;
+    if (NC == 256 || S::kThirdIsPair) return i * M;
+    return S::kThreads * (i >> 2) + (i & 3) * M;
+}
+template <int NC> __device__ __forceinline__ int fft_out_index(int t, int i) { return fft_out_base<NC>(t) + fft_out_const<NC>(i); }
+
 // The whole NC-point FFT for one frame.  On entry buf holds the input in slot order (slot = fft_slot_of_input(c)) at
 // padded positions and the frame's threads have synchronised; on exit v[] holds this thread's outputs and
 // fft_out_index() tells which.  The caller decides whether the outputs go back to buf (analysis) or out to memory.
@@ -144,54 +163,44 @@ template <int NC, bool kInverse>
 __device__ __forceinline__ void fft_frame(float2 (&v)[16], float2 *buf, int t, int group, const float2 *__restrict__ tw) {
     using S = FftShape<NC>;
     constexpr int T = S::kThreads;
+    {
+        float2 *b1 = buf + fft_pad(16 * t);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = buf[fft_pad(16 * t + j)];
-    fft_first_pass<NC, kInverse>(v, tw);
+        for (int j = 0; j < 16; ++j) v[j] = b1[j];
+        fft_first_pass<NC, kInverse>(v, tw);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) buf[fft_pad(16 * t + j)] = v[j];
+        for (int j = 0; j < 16; ++j) b1[j] = v[j];
+    }
     frame_sync<T>(group);
     {
         constexpr int M = S::kMid;
-        const int k = t & (M - 1), base = (t / M) * (16 * M) + k;
+        const int k = t & (M - 1);
+        float2 *b2 = buf + fft_pad((t / M) * (16 * M) + k);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = buf[fft_pad(base + j * M)];
+        for (int j = 0; j < 16; ++j) v[j] = b2[fft_pad(j * M)];
         fft_pair_pass<NC, M, kInverse>(v, k, tw);
         if (NC > 256) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) buf[fft_pad(base + j * M)] = v[j];
+            for (int j = 0; j < 16; ++j) b2[fft_pad(j * M)] = v[j];
         }
     }
     if (NC > 256) {
         frame_sync<T>(group);
         constexpr int M = S::kLast;
         if (S::kThirdIsPair) {
-            const int k = t & (M - 1), base = (t / M) * (16 * M) + k;
+            const int k = t & (M - 1);
+            const float2 *b3 = buf + fft_pad((t / M) * (16 * M) + k);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = buf[fft_pad(base + j * M)];
+            for (int j = 0; j < 16; ++j) v[j] = b3[fft_pad(j * M)];
             fft_pair_pass<NC, M, kInverse>(v, k, tw);
         } else {
+            const float2 *b3 = buf + fft_pad(t);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[4 * q + j] = buf[fft_pad(t + T * q + j * M)];
+                for (int j = 0; j < 4; ++j) v[4 * q + j] = b3[fft_pad(T * q + j * M)];
             fft_single_pass<NC, kInverse>(v, t, tw);
         }
-    }
-}
-
-// natural-order index of v[i] after fft_frame
-template <int NC> __device__ __forceinline__ int fft_out_index(int t, int i) {
-    using S = FftShape<NC>;
-    constexpr int T = S::kThreads;
-    if (NC == 256) {
-        constexpr int M = S::kMid;
-        return (t / M) * (16 * M) + (t & (M - 1)) + i * M;
-    } else if (S::kThirdIsPair) {
-        constexpr int M = S::kLast;
-        return (t / M) * (16 * M) + (t & (M - 1)) + i * M;
-    } else {
-        constexpr int M = S::kLast;
-        return t + T * (i >> 2) + (i & 3) * M;
     }
 }
 

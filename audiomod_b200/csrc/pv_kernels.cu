@@ -193,8 +193,9 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
     else { if (NC > 256) { frame_sync<T>(group); } frame_sync<T>(group); }
     frame_sync<T>(group);   // all reads of the last pass are done before the natural-order write-back
     if (active) {
+        float2 *bo = buf + fft_pad(fft_out_base<NC>(t));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) buf[fft_pad(fft_out_index<NC>(t, i))] = v[i];
+        for (int i = 0; i < 16; ++i) bo[fft_pad(fft_out_const<NC>(i))] = v[i];
     }
     frame_sync<T>(group);
     if (!active) return;
@@ -836,12 +837,15 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
     // un-shifted block; they land at (2o + N/2) mod N
     float *__restrict__ out = g.frames + ((int64_t)row * g.Fr + (k % g.Fr)) * N;
     const float2 *__restrict__ w2 = (const float2 *)p.window;
+    // the thread part of the output index never has the NC/2 bit, so the shift by NC/2 only touches the compile-time part
+    const int ob = fft_out_base<NC>(t);
+    const float2 *__restrict__ wb = w2 + ob;
+    float2 *__restrict__ outb = (float2 *)out + ob;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int o = fft_out_index<NC>(t, i);
-        const int oc = (o + NC / 2) & (NC - 1);
-        const float2 w = __ldg(&w2[oc]);
-        ((float2 *)out)[oc] = make_float2(v[i].x * w.x, v[i].y * w.y);
+        const int oc = fft_out_const<NC>(i) ^ (NC / 2);
+        const float2 w = __ldg(&wb[oc]);
+        outb[oc] = make_float2(v[i].x * w.x, v[i].y * w.y);
     }
 }
 
