@@ -291,11 +291,16 @@ struct Pipeline {
         return upload(b_whisper, ph.data(), sizeof(float) * n);
     }
 
-    // Frames [k0, k0+nf) of the rows in g; the schedule for them must be on the device.
-    void run_frames(const DevRows &g, long k0, int nf, cudaStream_t st) {
+    // Frames [k0, k0+nf) of the rows in g; the schedule for them must be on the device.  Three stages so that callers can
+    // put them on different streams: analysis | phase modification + synthesis | overlap-add + resampler.
+    void run_analyse(const DevRows &g, long k0, int nf, cudaStream_t st) {
+        Span *sp = span_begin(0, st);
+        launch_analyse(p, g, k0, nf, st);
+        span_end(sp, st); ++launches;
+    }
+    void run_modify_synth(const DevRows &g, long k0, int nf, cudaStream_t st) {
         const SliceRec *recs = b_recs.as<SliceRec>();
         Span *sp;
-        sp = span_begin(0, st); launch_analyse(p, g, k0, nf, st); span_end(sp, st); ++launches;
         if (d.robotic || d.whisper) {
             sp = span_begin(5, st);
             launch_fixed_phase(p, g, d.whisper ? b_whisper.as<float>() : nullptr, k0, nf, st);
@@ -306,10 +311,18 @@ struct Pipeline {
         sp = span_begin(2, st);
         launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st);
         span_end(sp, st); ++launches;
-        sp = span_begin(3, st);
+    }
+    void run_ola(const DevRows &g, long k0, int nf, cudaStream_t st) {
+        const SliceRec *recs = b_recs.as<SliceRec>();
+        Span *sp = span_begin(3, st);
         launch_ola_resample(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, table_run, max_consumed, b_runs.as<ResampleRun>(),
                             b_rsent.as<unsigned>(), b_rsfrac.as<float>(), run_origin, st);
         span_end(sp, st); ++launches;
+    }
+    void run_frames(const DevRows &g, long k0, int nf, cudaStream_t st) {
+        run_analyse(g, k0, nf, st);
+        run_modify_synth(g, k0, nf, st);
+        run_ola(g, k0, nf, st);
     }
 };
 
@@ -320,12 +333,17 @@ struct Workspace {
 
     // halo: frames before the current chunk that the overlap-add of the chunk (and of the resampler history before
     // it) still reads
-    int ensure(const Pipeline &pl, int rows_, int F_, int halo) {
+    // nbuf spectra buffers / (nbuf*F + halo) ring slots: nbuf = 2 lets the analysis of chunk c+1 and the overlap-add of
+    // chunk c-1 run while chunk c is in the phase / synthesis stage (see ChunkPipe)
+    int nbuf = 1;
+    size_t spec_stride = 0;   // floats between the spectra buffers
+    int ensure(const Pipeline &pl, int rows_, int F_, int halo, int nbuf_ = 1) {
         const DevPlan &p = pl.p;
-        rows = rows_; F = F_; Fr = F_ + halo;
+        rows = rows_; F = F_; nbuf = nbuf_; Fr = nbuf_ * F_ + halo;
         const int streams = rows / pl.d.cfg.channels;
-        CU(mag.ensure(sizeof(float) * (size_t)rows * F * p.Hp));
-        CU(phase.ensure(sizeof(float) * (size_t)rows * F * p.Hp));
+        spec_stride = (size_t)rows * F * p.Hp;
+        CU(mag.ensure(sizeof(float) * spec_stride * nbuf));
+        CU(phase.ensure(sizeof(float) * spec_stride * nbuf));
         CU(frames.ensure(sizeof(float) * (size_t)rows * Fr * p.N));
         CU(prev_phase.ensure(sizeof(float) * (size_t)rows * p.half));
         CU(prev_out.ensure(sizeof(float) * (size_t)rows * p.half));
@@ -344,8 +362,8 @@ struct Workspace {
         return PVGPU_OK;
     }
 
-    void bind(const Pipeline &pl, DevRows &g) const {
-        g.mag = mag.as<float>(); g.phase = phase.as<float>(); g.F = F;
+    void bind(const Pipeline &pl, DevRows &g, int buf = 0) const {
+        g.mag = mag.as<float>() + spec_stride * buf; g.phase = phase.as<float>() + spec_stride * buf; g.F = F;
         g.frames = frames.as<float>(); g.Fr = Fr;
         g.prev_phase = prev_phase.as<float>(); g.prev_out = prev_out.as<float>();
         g.peaks = peaks.as<int>(); g.maxpk = pl.max_peaks(); g.started = first.as<int>();
@@ -387,8 +405,11 @@ struct pvgpu_batch {
     // serial-in-time phase kernel of one group overlaps the FFT kernels of another, and -- for host buffers -- H2D,
     // kernels and D2H of different groups overlap.
     struct Ctx {
-        cudaStream_t st = nullptr;
+        cudaStream_t st = nullptr;       // analysis (and everything, when the stages are not overlapped)
+        cudaStream_t st_b = nullptr;     // phase modification + synthesis
+        cudaStream_t st_c = nullptr;     // overlap-add + resampler
         cudaEvent_t done = nullptr;
+        cudaEvent_t ev_an[4] = {}, ev_syn[4] = {}, ev_ola[4] = {};
         Workspace ws;
         DevBuf stage_in, stage_out;
     };
@@ -400,16 +421,24 @@ struct pvgpu_batch {
     cudaStream_t stream = nullptr;
     int64_t h2d = 0, d2h = 0;
     ~pvgpu_batch() {
-        for (auto &c : ctx) { if (c.st) cudaStreamDestroy(c.st); if (c.done) cudaEventDestroy(c.done); }
+        for (auto &c : ctx) {
+            if (c.st) cudaStreamDestroy(c.st);
+            if (c.st_b) cudaStreamDestroy(c.st_b);
+            if (c.st_c) cudaStreamDestroy(c.st_c);
+            if (c.done) cudaEventDestroy(c.done);
+            for (int i = 0; i < 4; ++i) { if (c.ev_an[i]) cudaEventDestroy(c.ev_an[i]); if (c.ev_syn[i]) cudaEventDestroy(c.ev_syn[i]); if (c.ev_ola[i]) cudaEventDestroy(c.ev_ola[i]); }
+        }
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
     std::vector<cudaEvent_t> ev_pool;   // chunk events of the time-sliced host pipeline
     bool time_sliced = true;
+    // stage overlap needs more than one context's worth of streams; contexts == 1 means strictly serial kernels (profiling)
+    bool overlap_stages() const { return n_contexts > 1; }
     size_t max_ws_bytes = (size_t)24 << 30;   // largest workspace a single group may take
     size_t ws_bytes_per_row() const {
-        return sizeof(float) * ((size_t)2 * frames_per_chunk * pl.p.Hp + (size_t)(frames_per_chunk + halo) * pl.p.N + 2 * (size_t)pl.p.half);
+        return sizeof(float) * ((size_t)4 * frames_per_chunk * pl.p.Hp + (size_t)(2 * frames_per_chunk + halo) * pl.p.N + 2 * (size_t)pl.p.half);
     }
     int run_for_chunk = 0;   // frames_per_chunk the resampler work lists were built for
     int prepare_runs() {
@@ -429,6 +458,77 @@ struct pvgpu_batch {
         return std::min(group, total);
     }
 };
+
+// All frame chunks of one group.  With `overlap` the three stages of a chunk run on the context's three streams:
+//   A  analysis of chunk c            (needs the spectra buffer c%2 free: synthesis of chunk c-2 done)
+//   B  phase core + synthesis of c    (needs A(c); its ring slots free: overlap-add of chunk c-2 done)
+//   C  overlap-add + resampler of c   (needs B(c))
+// so the latency-bound, serial-in-time phase kernel shares the SMs with the FFT-heavy kernels of its neighbours.
+// before(ci, k0, nf, stA) is called before the analysis of a chunk is enqueued on stA (e.g. to make it wait for an H2D
+// copy), after(ci, k0, nf, stC) once the chunk's overlap-add has been enqueued on stC (e.g. to start a D2H copy).
+// On return everything has been joined into ctx.st.
+template <class Before, class After>
+static int run_chunks(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, DevRows g, bool overlap, Before before, After after) {
+    Pipeline &pl = b->pl;
+    const int F = ctx.ws.F;
+    cudaStream_t sa = ctx.st, sb = overlap ? ctx.st_b : ctx.st, sc = overlap ? ctx.st_c : ctx.st;
+    if (overlap) {   // fork: B and C start after what is already queued on A (state reset, earlier groups)
+        CU(cudaEventRecord(ctx.done, sa));
+        CU(cudaStreamWaitEvent(sb, ctx.done, 0));
+        CU(cudaStreamWaitEvent(sc, ctx.done, 0));
+    }
+    long ci = 0;
+    for (long k0 = 0; k0 < b->n_slices; k0 += F, ++ci) {
+        const int nf = (int)std::min<long>(F, b->n_slices - k0);
+        const int e = (int)(ci & 3), e2 = (int)((ci + 2) & 3);   // e2: the slot chunk ci-2 used
+        ctx.ws.bind(pl, g, overlap ? (int)(ci & 1) : 0);
+        int rc = before(ci, k0, nf, sa);
+        if (rc) return rc;
+        if (overlap && ci >= 2) CU(cudaStreamWaitEvent(sa, ctx.ev_syn[e2], 0));
+        pl.run_analyse(g, k0, nf, sa);
+        if (overlap) {
+            CU(cudaEventRecord(ctx.ev_an[e], sa));
+            CU(cudaStreamWaitEvent(sb, ctx.ev_an[e], 0));
+            if (ci >= 2) CU(cudaStreamWaitEvent(sb, ctx.ev_ola[e2], 0));
+        }
+        pl.run_modify_synth(g, k0, nf, sb);
+        if (overlap) {
+            CU(cudaEventRecord(ctx.ev_syn[e], sb));
+            CU(cudaStreamWaitEvent(sc, ctx.ev_syn[e], 0));
+        }
+        pl.run_ola(g, k0, nf, sc);
+        if (overlap) CU(cudaEventRecord(ctx.ev_ola[e], sc));
+        if ((rc = after(ci, k0, nf, sc))) return rc;
+    }
+    if (overlap) {   // join
+        CU(cudaEventRecord(ctx.done, sb));
+        CU(cudaStreamWaitEvent(sa, ctx.done, 0));
+        CU(cudaEventRecord(ctx.done, sc));
+        CU(cudaStreamWaitEvent(sa, ctx.done, 0));
+    }
+    CU(cudaGetLastError());
+    return PVGPU_OK;
+}
+
+static DevRows group_rows_view(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int row0, int rows, int fmt) {
+    DevRows g{};
+    g.rows = rows; g.channels = b->cfg.channels;
+    g.in = d_in; g.in_stride = in_stride; g.in_base = 0; g.fmt = fmt;
+    g.n_in = b->d_nin.as<int64_t>() + row0;
+    g.n_out = b->d_nout.as<int64_t>() + row0;
+    g.out = d_out; g.out_stride = out_stride; g.out_base = 0;
+    return g;
+}
+
+// One group of rows on one context; on return the group's completion is ordered on ctx.st.
+static int batch_run_group(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride,
+                           int row0, int rows, int fmt) {
+    int rc;
+    ctx.ws.rows = rows;
+    if ((rc = ctx.ws.reset_state(b->pl, ctx.st))) return rc;
+    auto nop = [](long, long, int, cudaStream_t) { return (int)PVGPU_OK; };
+    return run_chunks(b, ctx, group_rows_view(b, d_in, in_stride, d_out, out_stride, row0, rows, fmt), b->overlap_stages(), nop, nop);
+}
 
 extern "C" {
 
@@ -475,7 +575,14 @@ int pvgpu_batch_create(const pvgpu_config *cfg, int n_streams, int64_t max_in_sa
     CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     for (auto &c : b->ctx) {
         CU(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c.st_b, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c.st_c, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        for (int i = 0; i < 4; ++i) {
+            CU(cudaEventCreateWithFlags(&c.ev_an[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c.ev_syn[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c.ev_ola[i], cudaEventDisableTiming));
+        }
     }
     *out = b.release();
     return PVGPU_OK;
@@ -569,29 +676,6 @@ int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_
     return PVGPU_OK;
 }
 
-// One group of rows on one context; everything is enqueued on ctx.st.
-static int batch_run_group(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride,
-                           int row0, int rows, int fmt) {
-    Pipeline &pl = b->pl;
-    int rc;
-    ctx.ws.rows = rows;
-    if ((rc = ctx.ws.reset_state(pl, ctx.st))) return rc;
-    DevRows g{};
-    g.rows = rows; g.channels = b->cfg.channels;
-    g.in = d_in; g.in_stride = in_stride; g.in_base = 0; g.fmt = fmt;
-    g.n_in = b->d_nin.as<int64_t>() + row0;
-    g.n_out = b->d_nout.as<int64_t>() + row0;
-    g.out = d_out; g.out_stride = out_stride; g.out_base = 0;
-    ctx.ws.bind(pl, g);
-    const int F = ctx.ws.F;
-    for (long k0 = 0; k0 < b->n_slices; k0 += F) {
-        const int nf = (int)std::min<long>(F, b->n_slices - k0);
-        pl.run_frames(g, k0, nf, ctx.st);
-    }
-    CU(cudaGetLastError());
-    return PVGPU_OK;
-}
-
 int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt, void *cuda_stream) {
     if (!b || !d_in || !d_out) return fail(PVGPU_EINVAL, "null argument");
     if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
@@ -605,7 +689,7 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
     const int n_ctx = std::min(n_groups, b->n_contexts);
     int rc;
     for (int i = 0; i < n_ctx; ++i)
-        if ((rc = b->ctx[i].ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
+        if ((rc = b->ctx[i].ws.ensure(b->pl, group, b->frames_per_chunk, b->halo, b->overlap_stages() ? 2 : 1))) return rc;
     if ((rc = b->prepare_runs())) return rc;
     b->pl.launches = 0;
     // fork: the contexts start after everything already queued on the caller's stream
@@ -671,9 +755,10 @@ static int run_host_timesliced(pvgpu_batch *b, const void *const *in_rows, void 
     Pipeline &pl = b->pl;
     const int total_rows = b->n_streams * b->cfg.channels;
     pvgpu_batch::Ctx &c = b->ctx[0];
-    cudaStream_t s_comp = c.st, s_in = b->ctx[1].st, s_out = b->ctx[2].st;
+    cudaStream_t s_in = b->ctx[1].st, s_out = b->ctx[2].st;
+    const bool overlap = b->overlap_stages();
     int rc;
-    if ((rc = c.ws.ensure(pl, total_rows, b->frames_per_chunk, b->halo))) return rc;
+    if ((rc = c.ws.ensure(pl, total_rows, b->frames_per_chunk, b->halo, overlap ? 2 : 1))) return rc;
     CU(c.stage_in.ensure(esz * (size_t)total_rows * in_stride));
     CU(c.stage_out.ensure(esz * (size_t)total_rows * out_stride));
     const int F = c.ws.F;
@@ -684,42 +769,39 @@ static int run_host_timesliced(pvgpu_batch *b, const void *const *in_rows, void 
         b->ev_pool.push_back(e);
     }
     c.ws.rows = total_rows;
-    if ((rc = c.ws.reset_state(pl, s_comp))) return rc;
-    DevRows g{};
-    g.rows = total_rows; g.channels = b->cfg.channels;
-    g.in = c.stage_in.p; g.in_stride = in_stride; g.in_base = 0; g.fmt = fmt;
-    g.n_in = b->d_nin.as<int64_t>(); g.n_out = b->d_nout.as<int64_t>();
-    g.out = c.stage_out.p; g.out_stride = out_stride; g.out_base = 0;
-    c.ws.bind(pl, g);
+    if ((rc = c.ws.reset_state(pl, c.st))) return rc;
     const int64_t n_in = b->n_in[0], n_out = b->n_out[0];
     int64_t in_done = 0, out_done = 0;
     const std::vector<SliceRec> &recs = pl.h_recs;
-    for (long ci = 0, k0 = 0; k0 < b->n_slices; ++ci, k0 += F) {
-        const int nf = (int)std::min<long>(F, b->n_slices - k0);
+    auto before = [&](long ci, long k0, int nf, cudaStream_t sa) -> int {
         const int64_t need = std::min<int64_t>(n_in, (int64_t)(k0 + nf - 1) * pl.p.hop + pl.p.N);
         if (need > in_done) {
             CU(cudaMemcpy2DAsync((char *)c.stage_in.p + in_done * esz, in_stride * esz, (const char *)in_rows[0] + in_done * esz, (size_t)in_pitch,
                                  (size_t)(need - in_done) * esz, total_rows, cudaMemcpyHostToDevice, s_in));
             b->h2d += (int64_t)(need - in_done) * esz * total_rows;
             in_done = need;
+            CU(cudaEventRecord(b->ev_pool[2 * ci], s_in));
+            CU(cudaStreamWaitEvent(sa, b->ev_pool[2 * ci], 0));
         }
-        CU(cudaEventRecord(b->ev_pool[2 * ci], s_in));
-        CU(cudaStreamWaitEvent(s_comp, b->ev_pool[2 * ci], 0));
-        pl.run_frames(g, k0, nf, s_comp);
-        CU(cudaEventRecord(b->ev_pool[2 * ci + 1], s_comp));
-        CU(cudaStreamWaitEvent(s_out, b->ev_pool[2 * ci + 1], 0));
+        return PVGPU_OK;
+    };
+    auto after = [&](long ci, long k0, int nf, cudaStream_t sc) -> int {
         const SliceRec &last = recs[k0 + nf - 1 - pl.recs_base];
         const int64_t avail = std::min<int64_t>(n_out, last.out_off + ((last.flags & 1) ? 0 : last.n_write));
         if (avail > out_done) {
+            CU(cudaEventRecord(b->ev_pool[2 * ci + 1], sc));
+            CU(cudaStreamWaitEvent(s_out, b->ev_pool[2 * ci + 1], 0));
             CU(cudaMemcpy2DAsync((char *)out_rows[0] + out_done * esz, (size_t)out_pitch, (const char *)c.stage_out.p + out_done * esz, out_stride * esz,
                                  (size_t)(avail - out_done) * esz, total_rows, cudaMemcpyDeviceToHost, s_out));
             b->d2h += (int64_t)(avail - out_done) * esz * total_rows;
             out_done = avail;
         }
-    }
-    CU(cudaGetLastError());
+        return PVGPU_OK;
+    };
+    if ((rc = run_chunks(b, c, group_rows_view(b, c.stage_in.p, in_stride, c.stage_out.p, out_stride, 0, total_rows, fmt), overlap, before, after)))
+        return rc;
     CU(cudaStreamSynchronize(s_in));
-    CU(cudaStreamSynchronize(s_comp));
+    CU(cudaStreamSynchronize(c.st));
     CU(cudaStreamSynchronize(s_out));
     return PVGPU_OK;
 }
@@ -753,7 +835,7 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
     const int n_ctx = std::min(n_groups, b->n_contexts);
     for (int i = 0; i < n_ctx; ++i) {
         pvgpu_batch::Ctx &c = b->ctx[i];
-        if ((rc = c.ws.ensure(b->pl, group, b->frames_per_chunk, b->halo))) return rc;
+        if ((rc = c.ws.ensure(b->pl, group, b->frames_per_chunk, b->halo, b->overlap_stages() ? 2 : 1))) return rc;
         CU(c.stage_in.ensure(esz * (size_t)group * in_stride));
         CU(c.stage_out.ensure(esz * (size_t)group * out_stride));
     }
