@@ -144,6 +144,30 @@ def test_batch_ragged_matches_oracle(A, oracle, case):
         assert_parity(y, r, f"{name}[{i}]")
 
 
+@pytest.mark.parametrize("kw,sr,ch", [
+    (dict(semitones=5.0, mode=0, coremode=1, fftsize=256), 22050, 2),       # sizes outside 512..8192 take the generic kernels
+    (dict(timeratio=1.25, mode=5, coremode=1, fftsize=16384), 48000, 1),
+    (dict(semitones=-3.0, mode=2, fftsize=1000), 44100, 1),                 # rounded up to 1024 like the reference
+    (dict(semitones=2.0, mode=0, coremode=1, fftsize=2048, hopsize=300), 44100, 2),   # explicit analysis hop
+    (dict(timeratio=0.5, mode=5, coremode=0, fftsize=1024, hopsize=128), 44100, 1),
+    (dict(semitones=24.0, mode=0, coremode=1, fftsize=1024), 44100, 1),     # two octaves up: oversample 4 table
+    (dict(semitones=-12.0, mode=0, coremode=1, fftsize=2048), 44100, 1),    # octave down: up-sampling resampler
+])
+def test_unusual_sizes_and_hops(A, oracle, kw, sr, ch):
+    xs = [make_input("x", sr, ch, 0.7 - 0.2 * i, 800 + i) for i in range(2)]
+    ref = [oracle.run_offline(x, sr, **kw) for x in xs]
+    tr, st, mode, core, fft = ctor_args(kw)
+    b = A.PhaseVocoderBatch(2, xs[0].shape[1], sr, ch, tr, st, mode, core, fft, kw.get("hopsize", 0))
+    ys = b.run(xs)
+    b.close()
+    for i, (y, r) in enumerate(zip(ys, ref)):
+        assert_parity(y, r, f"{kw}[{i}]")
+    pv = A.phasevocoder(sr, ch, tr, st, mode, core, fft, kw.get("hopsize", 0))
+    y = _cli_protocol(pv, xs[1], sr, mode)
+    pv.close()
+    assert_parity(y, ref[1], f"{kw} stream")
+
+
 def test_empty_and_tiny_streams(A, oracle):
     sr = 44100
     xs = [np.zeros((1, 0), np.float32), make_input("x", sr, 1, 0.001, 1), make_input("x", sr, 1, 0.05, 2), make_input("x", sr, 1, 0.3, 3)]
