@@ -713,11 +713,13 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
 // spaced, one copy per row otherwise
 static int copy_rows(void *dev, int64_t dev_stride, const void *const *host_rows, int r0, int rows, const int64_t *lens, int C, bool to_device,
                      size_t esz, cudaStream_t st, int64_t *bytes) {
+    // the 2-D copy moves the same number of elements for every row, so it is only used when all rows of the block have the
+    // same length (otherwise it would run past the end of the shorter host rows)
     bool regular = rows > 1;
     const ptrdiff_t pitch = rows > 1 ? (const char *)host_rows[r0 + 1] - (const char *)host_rows[r0] : 0;
-    int64_t maxlen = 0;
+    const int64_t maxlen = lens[r0 / C];
     for (int r = 0; r < rows; ++r) {
-        maxlen = std::max(maxlen, lens[(r0 + r) / C]);
+        if (lens[(r0 + r) / C] != maxlen) regular = false;
         if (r + 1 < rows && (const char *)host_rows[r0 + r + 1] - (const char *)host_rows[r0 + r] != pitch) regular = false;
     }
     if (regular && pitch >= (ptrdiff_t)(maxlen * esz) && maxlen > 0) {
