@@ -428,8 +428,8 @@ __global__ void k_phase_core(const DevPlan p, const DevRows g, const SliceRec *_
 //    already in its registers, and the region of a bin is one of the two peaks around the thread's first bin -- no search;
 //  * current / previous peak lists ping-pong instead of being copied; four block barriers per (frame, channel).
 // ------------------------------------------------------------------------------------------------
-template <int E>
-__global__ void __launch_bounds__(512) k_phase_lock_t(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base, long k0,
+template <int E, int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_phase_lock_t(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base, long k0,
                                                       int nframes) {
     static_assert(E == 4 || E == 8, "bins per thread");
     constexpr int kMaxOwn = (E + 2) / 3;
@@ -876,7 +876,7 @@ struct OlaTables {
 };
 
 template <int OV>   // sinc-table oversampling of the interpolated resampler mode; 0 = direct table or no resampler
-__global__ void __launch_bounds__(256) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
+__global__ void __launch_bounds__(256, 5) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
                                                       int64_t norm_base, long recs_base, long k0, int nf, int run, int max_in, const ResampleRun *__restrict__ runs,
                                                       const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, long run_origin) {
     extern __shared__ float4 smem4[];
@@ -1059,8 +1059,9 @@ cudaError_t configure_kernels() {
     if ((e = cudaFuncSetAttribute(k_ola_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_ola_resample<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_ola_resample<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_phase_lock_t<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_phase_lock_t<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_phase_lock_t<8, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -1097,8 +1098,9 @@ void launch_phase_core(const DevPlan &p, const DevRows &g, int coremode, const S
     if (coremode == 1 && (p.N == 512 || p.N == 1024 || p.N == 2048 || p.N == 4096 || p.N == 8192)) {
         const int E = p.N == 8192 ? 8 : 4;
         const size_t sm = sizeof(float) * ((size_t)2 * p.half + 8 + (size_t)2 * g.channels * p.half + (size_t)4 * g.maxpk + 1 + 32 + 8);
-        if (E == 4) k_phase_lock_t<4><<<streams, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
-        else k_phase_lock_t<8><<<streams, p.half / 8, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+        if (E == 8) k_phase_lock_t<8, 512, 2><<<streams, p.half / 8, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+        else if (p.half / 4 > 256) k_phase_lock_t<4, 512, 2><<<streams, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+        else k_phase_lock_t<4, 256, 4><<<streams, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
         return;
     }
     const size_t sm = smem_phase_core(p, g.channels, g.maxpk);
