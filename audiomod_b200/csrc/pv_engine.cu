@@ -201,6 +201,19 @@ struct Pipeline {
 
     int max_peaks() const { return p.half / 3 + 2; }
 
+    // Modes that never use the analysis phase keep Cartesian spectra (no sqrtf / atan2f per bin in the analysis kernel); only
+    // the templated FFT sizes have that variant.
+    bool cartesian() const {
+        const bool templated = p.N == 512 || p.N == 1024 || p.N == 2048 || p.N == 4096 || p.N == 8192;
+        return templated && (d.robotic || d.whisper || d.vocoder || d.constant_mode);
+    }
+    void apply_mode(DevRows &g) const {
+        g.spec = cartesian() ? 1 : 0;
+        g.synth_kind = d.vocoder ? 0 : d.robotic ? 1 : d.whisper ? 2 : d.constant_mode ? 3 : 0;
+        g.whisper = (d.whisper && cartesian()) ? b_whisper.as<float>() : nullptr;
+        if (!cartesian()) g.synth_kind = 0;   // polar spectra: k_fixed_phase has already written the phases
+    }
+
     // Upload the slice records [first, first+count) and the normalisers from norm_first on.
     int upload_schedule(const Scheduler &s, cudaStream_t st) {
         const auto &recs = s.recs();
@@ -301,7 +314,7 @@ struct Pipeline {
     void run_modify_synth(const DevRows &g, long k0, int nf, cudaStream_t st) {
         const SliceRec *recs = b_recs.as<SliceRec>();
         Span *sp;
-        if (d.robotic || d.whisper) {
+        if ((d.robotic || d.whisper) && !g.spec) {
             sp = span_begin(5, st);
             launch_fixed_phase(p, g, d.whisper ? b_whisper.as<float>() : nullptr, k0, nf, st);
             span_end(sp, st); ++launches;
@@ -517,6 +530,7 @@ static DevRows group_rows_view(pvgpu_batch *b, const void *d_in, int64_t in_stri
     g.n_in = b->d_nin.as<int64_t>() + row0;
     g.n_out = b->d_nout.as<int64_t>() + row0;
     g.out = d_out; g.out_stride = out_stride; g.out_base = 0;
+    b->pl.apply_mode(g);
     return g;
 }
 
@@ -1041,6 +1055,7 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
         CU(cudaMemcpyAsync(pl.b_whisper.p, ph.data(), sizeof(float) * n, cudaMemcpyHostToDevice, s->st));
         CU(cudaStreamSynchronize(s->st));
     }
+    pl.apply_mode(g);   // after the whisper table has its final address
     if (pl.d.vocoder) {
         const int64_t clen = (int64_t)s->car_tail.size();
         CU(s->d_car.ensure(sizeof(float) * (size_t)std::max<int64_t>(clen, 1)));

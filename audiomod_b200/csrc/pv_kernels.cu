@@ -128,7 +128,7 @@ __global__ void k_analyse(const DevPlan p, const DevRows g, long k0) {
 // k_analyse_t<N>: register-tiled version for N = 512..8192 (pv_fft.cuh).  T = N/32 threads own a frame; a CTA of
 // max(T, 256) threads handles 256/T consecutive frames of the chunk.
 // ------------------------------------------------------------------------------------------------
-template <int N, bool kS16>
+template <int N, bool kS16, bool kCart>
 __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(const DevPlan p, const DevRows g, long k0, int nf, int total) {
     constexpr int NC = N / 2;
     using S = FftShape<NC>;
@@ -224,10 +224,15 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
             ar = __fmul_rn(__fadd_rn(f1k.x, tw.x), 0.5f); ai = __fmul_rn(__fadd_rn(f1k.y, tw.y), 0.5f);
             br = __fmul_rn(__fsub_rn(f1k.x, tw.x), 0.5f); bi = __fmul_rn(__fsub_rn(tw.y, f1k.y), 0.5f);
         }
-        mag[kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
-        ph[kk] = pv_atan2f_fast(ai, ar);
-        mag[NC - kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
-        ph[NC - kk] = pv_atan2f_fast(bi, br);
+        if (kCart) {   // Cartesian spectra for the modes that never look at the analysis phase
+            mag[kk] = ar; ph[kk] = ai;
+            mag[NC - kk] = br; ph[NC - kk] = bi;
+        } else {
+            mag[kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)));
+            ph[kk] = pv_atan2f_fast(ai, ar);
+            mag[NC - kk] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+            ph[NC - kk] = pv_atan2f_fast(bi, br);
+        }
     }
     if (t == 0) {   // bin NC/2 pairs with itself; the reference writes it twice and the second write wins (kiss_fftr.c:116-119)
         const float2 fpk = buf[fft_pad(NC / 2)];
@@ -235,8 +240,12 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
         const float2 f1k = cadd_rn(fpk, fpnk), f2k = csub_rn(fpk, fpnk);
         const float2 tw = cmul_rn(f2k, __ldg(&stw[NC / 2]));
         const float br = __fmul_rn(__fsub_rn(f1k.x, tw.x), 0.5f), bi = __fmul_rn(__fsub_rn(tw.y, f1k.y), 0.5f);
-        mag[NC / 2] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
-        ph[NC / 2] = pv_atan2f_fast(bi, br);
+        if (kCart) {
+            mag[NC / 2] = br; ph[NC / 2] = bi;
+        } else {
+            mag[NC / 2] = __fsqrt_rn(__fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)));
+            ph[NC / 2] = pv_atan2f_fast(bi, br);
+        }
     }
 }
 
@@ -721,7 +730,16 @@ __global__ void k_synthesise(const DevPlan p, const DevRows g, const float *__re
 struct SynthBinLoader {
     const DevPlan &p;
     const float *__restrict__ gmag, *__restrict__ gph, *__restrict__ cmag, *__restrict__ cph;
-    // magnitude (before the 1/N scale) and phase of packed bin i after the mode's spectral modification
+    const float *__restrict__ wphase;   // whisper phases of this (slice, channel)
+    int spec, kind;                     // DevRows::spec / DevRows::synth_kind
+    // analysis magnitude of bin i (FFT.cc:2624); with Cartesian spectra it is formed here, with the same operations
+    __device__ __forceinline__ float in_mag(int i) const {
+        if (!spec) return gmag[i];
+        const float r = gmag[i], q = gph[i];
+        return __fsqrt_rn(__fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q)));
+    }
+    // (magnitude before the 1/N scale, phase) of packed bin i after the mode's spectral modification; for the constant
+    // mode on Cartesian spectra the pair is (re, im) and finish() only scales it
     __device__ __forceinline__ float2 load(int i) const {
         const int hs = p.half;
         float m, ph;
@@ -734,9 +752,15 @@ struct SynthBinLoader {
             } else if (band_len > 0) {
                 const int bs = (i / band_len) * band_len;
                 float mean = 0.f;
-                for (int e = 0; e < band_len; ++e) mean = __fadd_rn(mean, gmag[bs + e]);
+                for (int e = 0; e < band_len; ++e) mean = __fadd_rn(mean, in_mag(bs + e));
                 m = __fmul_rn(m, __fdiv_rn(mean, (float)(band_len * 2)));
             }
+        } else if (kind == 1) {         // roboticSlice (:805-812)
+            m = in_mag(i); ph = 0.f;
+        } else if (kind == 2) {         // whisperSlice (:814-822)
+            m = in_mag(i); ph = wphase[i];
+        } else if (kind == 3 && spec) { // constant mode: the spectrum goes back unchanged
+            m = gmag[i]; ph = gph[i];
         } else if (p.freq_comp != 0.f) {  // freqCompSlice (:842-923) as a gather
             if (p.freq_comp > 1.0f || i < hs) {
                 const int src = __float2int_rn(__fmul_rn((float)i, p.freq_comp));
@@ -759,6 +783,8 @@ struct SynthBinLoader {
     // 1/N scale (:1024) and polar -> cartesian (FFT.cc:2711-2721)
     __device__ __forceinline__ float2 finish(float2 mp) const {
         const float m = __fmul_rn(mp.x, p.inv_n);
+        if (kind == 1 && cmag == nullptr) return make_float2(m, 0.f);                          // cosf(0) = 1, sinf(0) = 0
+        if (kind == 3 && spec && cmag == nullptr) return make_float2(m, __fmul_rn(mp.y, p.inv_n));   // (re, im) / N
         float sn, cs;
         sincosf(mp.y, &sn, &cs);
         return make_float2(m * cs, m * sn);
@@ -783,7 +809,8 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
     if (active) {
         const int64_t so = ((int64_t)row * g.F + f) * p.Hp;
         const int64_t co = (int64_t)(k - g.aux_base) * p.Hp;
-        const SynthBinLoader bin{p, g.mag + so, g.phase + so, car_mag ? car_mag + co : nullptr, car_mag ? car_phase + co : nullptr};
+        const float *wph = g.whisper ? g.whisper + ((int64_t)(k - g.aux_base) * g.channels + row % g.channels) * p.H : nullptr;
+        const SynthBinLoader bin{p, g.mag + so, g.phase + so, car_mag ? car_mag + co : nullptr, car_mag ? car_phase + co : nullptr, wph, g.spec, g.synth_kind};
         const float2 *__restrict__ stw = p.stw_inv;
         // inverse real-FFT pre-pass (kiss_fftr.c:123-159).  All loads of the thread's bins are issued before any of the
         // (long) sincos evaluations so their latency overlaps.
@@ -1071,8 +1098,15 @@ template <int N> static void launch_analyse_t(const DevPlan &p, const DevRows &g
     using S = FftShape<N / 2>;
     constexpr int T = S::kThreads, G = (T >= 256) ? 1 : 256 / T;
     const int total = nframes * g.rows;
-    if (g.fmt) k_analyse_t<N, true><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, k0, nframes, total);
-    else k_analyse_t<N, false><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, k0, nframes, total);
+    const int grid = (total + G - 1) / G, block = T >= 256 ? T : 256;
+    const size_t sm = sizeof(float2) * G * S::kPadded;
+    if (g.spec) {
+        if (g.fmt) k_analyse_t<N, true, true><<<grid, block, sm, st>>>(p, g, k0, nframes, total);
+        else k_analyse_t<N, false, true><<<grid, block, sm, st>>>(p, g, k0, nframes, total);
+    } else {
+        if (g.fmt) k_analyse_t<N, true, false><<<grid, block, sm, st>>>(p, g, k0, nframes, total);
+        else k_analyse_t<N, false, false><<<grid, block, sm, st>>>(p, g, k0, nframes, total);
+    }
 }
 
 void launch_analyse(const DevPlan &p, const DevRows &g, long k0, int nframes, cudaStream_t st) {

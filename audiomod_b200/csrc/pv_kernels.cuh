@@ -52,6 +52,10 @@ struct DevRows {
     int maxpk;
     int *started;             // [streams] 0 until the first slice of the stream went through the core
     long aux_base;            // slice index of element 0 of the whisper table / carrier spectra
+    int spec;                 // 0: spectra are (mag, phase); 1: Cartesian (re in mag[], im in phase[]) -- modes that never use the
+                              //    analysis phase (robotic, whisper, vocoder, constant) skip sqrtf/atan2f in the analysis kernel
+    int synth_kind;           // 0: phases come from the spectra; 1: robotic (phase 0); 2: whisper (phase table); 3: constant
+    const float *whisper;     // [slices][channels][H] phases of the whisper mode (indexed by absolute slice - aux_base)
 };
 
 void launch_analyse(const DevPlan &p, const DevRows &g, long k0, int nframes, cudaStream_t st);
