@@ -314,10 +314,12 @@ struct Pipeline {
     void run_modify_synth(const DevRows &g, long k0, int nf, cudaStream_t st) {
         const SliceRec *recs = b_recs.as<SliceRec>();
         Span *sp;
-        if ((d.robotic || d.whisper) && !g.spec) {
+        if (d.robotic || d.whisper) {
+            if (g.spec) { /* phases are produced inside the synthesis kernel */ } else {
             sp = span_begin(5, st);
             launch_fixed_phase(p, g, d.whisper ? b_whisper.as<float>() : nullptr, k0, nf, st);
             span_end(sp, st); ++launches;
+            }
         } else if (!d.vocoder && !d.constant_mode) {
             sp = span_begin(1, st); launch_phase_core(p, g, d.cfg.coremode, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches;
         }
