@@ -29,6 +29,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SR, SEMITONES, FFT, COREMODE, MODE = 44100, 7.0, 2048, 1, 0
+CHANNELS, TIMERATIO = 1, 1.0
+# The judged line is cfg4 (the default).  The other BASELINE.json configurations can be timed with --workload for the
+# notes in profiles/; they are parity-test cases, not bench lines.
+WORKLOADS = {   # name: (sr, channels, timeratio, semitones, mode, coremode, fftsize, default streams)
+    "cfg4": (44100, 1, 1.0, 7.0, 0, 1, 2048, 4096),
+    "cfg1": (44100, 2, 1.0, 4.0, 0, 1, 2048, 2048),
+    "cfg2": (48000, 2, 1.5, 0.0, 5, 1, 4096, 1024),
+    "cfg3-formant": (44100, 1, 1.0, 4.0, 2, 1, 2048, 4096),
+    "cfg3-gender": (44100, 1, 1.0, -4.0, 1, 1, 2048, 4096),
+    "cfg5-robotic-2048": (44100, 2, 1.0, 0.0, 6, 1, 2048, 1024),
+    "cfg5-whisper-2048": (44100, 2, 1.0, 0.0, 7, 1, 2048, 1024),
+    "cfg5-vocoder-2048": (44100, 2, 1.0, 0.0, 3, 1, 2048, 1024),
+    "cfg5-robotic-512": (44100, 2, 1.0, 0.0, 6, 1, 512, 1024),
+    "cfg5-robotic-8192": (44100, 2, 1.0, 0.0, 6, 1, 8192, 1024),
+}
 METRIC = "audio-sec/sec, 2048-pt PV pitch-shift, batched streams"
 UNIT = "audio-s/s"
 
@@ -38,7 +53,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU")
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--secs", type=float, default=10.0)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-chunk", type=int, default=0)
@@ -47,14 +63,20 @@ def parse():
     ap.add_argument("--cpu-streams-per-core", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    global SR, CHANNELS, TIMERATIO, SEMITONES, MODE, COREMODE, FFT
+    SR, CHANNELS, TIMERATIO, SEMITONES, MODE, COREMODE, FFT, default_streams = WORKLOADS[args.workload]
+    if args.streams <= 0:
+        args.streams = default_streams
+    return args
 
 
 def workload_config(args, n_gpus):
-    return {"workload": f"{args.streams} synthetic mono {SR / 1000:g} kHz {args.secs:g} s streams per GPU, +{SEMITONES:g} semitones, "
-                        f"coremode {COREMODE}, FFT {FFT} (BASELINE.json configs[3])",
+    return {"workload": f"{args.workload}: {args.streams} synthetic {'mono' if CHANNELS == 1 else 'stereo'} {SR / 1000:g} kHz {args.secs:g} s streams per GPU, "
+                        f"time ratio {TIMERATIO:g}, {SEMITONES:+g} semitones, mode {MODE}, coremode {COREMODE}, FFT {FFT}"
+                        + (" (BASELINE.json configs[3])" if args.workload == "cfg4" else ""),
             "streams_per_gpu": args.streams, "stream_seconds": args.secs, "sample_rate": SR, "semitones": SEMITONES, "fftsize": FFT,
-            "coremode": COREMODE, "channels": 1, "n_gpus": n_gpus, "sharding": "streams split across GPUs, no collective",
+            "coremode": COREMODE, "channels": CHANNELS, "time_ratio": TIMERATIO, "mode": MODE, "n_gpus": n_gpus, "sharding": "streams split across GPUs, no collective",
             "l2": "inputs (7.2 GB/GPU at the default size) exceed the 126 MB L2; no explicit flush"}
 
 
@@ -66,13 +88,13 @@ def cpu_run(n_streams: int, secs: float, cores: int):
     """Process n_streams synthetic streams on `cores` host cores; returns (audio-s/s, kind, seconds)."""
     from audiomod_b200.synth import synth
     from oracle import pv_oracle as O
-    xs = [synth(4000 + i, SR, secs, 1) for i in range(n_streams)]
+    xs = [synth(4000 + i, SR, secs, CHANNELS) for i in range(n_streams)]
     if O.have_ref():
         kind = "reference"
         with tempfile.TemporaryDirectory(prefix="pvbench_") as d:
             for i, x in enumerate(xs):
                 x.tofile(os.path.join(d, f"i{i}.f32"))
-            cmds = [[O.REF_DRV, str(SR), "1", "1.0", repr(SEMITONES), str(MODE), str(COREMODE), str(FFT),
+            cmds = [[O.REF_DRV, str(SR), str(CHANNELS), repr(TIMERATIO), repr(SEMITONES), str(MODE), str(COREMODE), str(FFT),
                      os.path.join(d, f"i{i}.f32"), os.path.join(d, f"o{i}.f32")] for i in range(n_streams)]
             t0 = time.perf_counter()
             running, nxt = [], 0
@@ -97,7 +119,7 @@ def cpu_run(n_streams: int, secs: float, cores: int):
 
 def _port_one(x):
     from oracle import pv_oracle as O
-    return O.run_offline(x, SR, semitones=SEMITONES, mode=MODE, coremode=COREMODE, fftsize=FFT).shape[1]
+    return O.run_offline(x, SR, timeratio=TIMERATIO, semitones=SEMITONES, mode=MODE, coremode=COREMODE, fftsize=FFT).shape[1]
 
 
 def reference_arm(args):
@@ -237,11 +259,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    S, n = args.streams, int(round(SR * args.secs))
+    n = int(round(SR * args.secs))
+    n_streams = args.streams
+    S = n_streams * CHANNELS          # channel rows
     stride = (n + 3) & ~3
     d_in = torch.zeros((S, stride), dtype=torch.float32, device=dev)
     d_in[:, :n] = make_inputs(torch, dev, S, n, 1234 + rank)
-    batch = A.PhaseVocoderBatch(S, n, SR, 1, 1.0, SEMITONES, MODE, COREMODE, FFT, device=local)
+    batch = A.PhaseVocoderBatch(n_streams, n, SR, CHANNELS, TIMERATIO, SEMITONES, MODE, COREMODE, FFT, device=local)
     if args.frames_per_chunk or args.rows_per_group or args.contexts:
         batch.tune(args.frames_per_chunk, args.rows_per_group, args.contexts)
     n_out = batch.plan(n)
@@ -286,7 +310,7 @@ def main():
     batch.profile(False)
     batch.tune(contexts=args.contexts or 3)
     ms_step = ms_total / args.steps
-    audio_sec_per_step = world * S * args.secs
+    audio_sec_per_step = world * n_streams * args.secs
     value = audio_sec_per_step / (ms_step / 1e3)
     checksum = float(d_out[:, :int(n_out.min())].double().abs().mean().item())
 
@@ -296,7 +320,8 @@ def main():
     shift = hop * info["hs_ratio"]
     per_frame = {"analyse": 4 * (hop + 2 * H), "phase_core": 4 * (2 * H + half), "synthesise": 4 * (2 * H + N),
                  "ola_resample": 4 * (N + shift / info["pitch_scale"])}
-    dom = max((k for k in per_frame if ktimes[k][1] > 0), key=lambda k: ktimes[k][0])
+    per_frame["fixed_phase"] = 4 * H
+    dom = max((k for k in per_frame if ktimes.get(k, (0, 0))[1] > 0), key=lambda k: ktimes[k][0])
     dom_ms, dom_launches = ktimes[dom]
     bytes_total = per_frame[dom] * slices * S * args.steps
     achieved = bytes_total / (dom_ms / 1e3) / 1e9
@@ -319,7 +344,7 @@ def main():
                 "kernel_share_of_step": dom_ms / max(kernel_ms_sum, 1e-9),
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
                 "serialised_ms_per_step": ms_serial_step,
-                "compulsory_io_frac": (8.0 * n * S) / (ms_step / 1e3) / 1e9 / peak}
+                "compulsory_io_frac": (4.0 * (n + float(n_out.max())) * S) / (ms_step / 1e3) / 1e9 / peak}
 
     # ---- end to end through the host-buffer entry point ----
     e2e = None
