@@ -203,13 +203,18 @@ struct Pipeline {
 
     // Modes that never use the analysis phase keep Cartesian spectra (no sqrtf / atan2f per bin in the analysis kernel); only
     // the templated FFT sizes have that variant.
+    // The phase-locked core of the plain shift / stretch modes also runs on Cartesian spectra (k_phase_lock_c): locking a
+    // region is one rotation of its bins, and the analysis phase is only ever needed at the peaks.
+    bool cartesian_lock() const {
+        return d.cfg.coremode == 1 && !(d.robotic || d.whisper || d.vocoder || d.constant_mode) && p.freq_comp == 0.f;
+    }
     bool cartesian() const {
         const bool templated = p.N == 512 || p.N == 1024 || p.N == 2048 || p.N == 4096 || p.N == 8192;
-        return templated && (d.robotic || d.whisper || d.vocoder || d.constant_mode);
+        return templated && (d.robotic || d.whisper || d.vocoder || d.constant_mode || cartesian_lock());
     }
     void apply_mode(DevRows &g) const {
         g.spec = cartesian() ? 1 : 0;
-        g.synth_kind = d.vocoder ? 0 : d.robotic ? 1 : d.whisper ? 2 : d.constant_mode ? 3 : 0;
+        g.synth_kind = d.vocoder ? 0 : d.robotic ? 1 : d.whisper ? 2 : d.constant_mode ? 3 : cartesian_lock() ? 4 : 0;
         g.whisper = (d.whisper && cartesian()) ? b_whisper.as<float>() : nullptr;
         if (!cartesian()) g.synth_kind = 0;   // polar spectra: k_fixed_phase has already written the phases
     }
@@ -320,6 +325,14 @@ struct Pipeline {
             launch_fixed_phase(p, g, d.whisper ? b_whisper.as<float>() : nullptr, k0, nf, st);
             span_end(sp, st); ++launches;
             }
+        } else if (g.spec && cartesian_lock()) {
+            // phase-locked core on Cartesian spectra: frame-parallel peak / link / advance records, then the serial chain
+            sp = span_begin(6, st); launch_lock_peaks(p, g, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches;
+            // the chunk's last frame is what the next launch links to (before the chain touches classic frames in place)
+            const size_t pitch = sizeof(float) * (size_t)g.F * p.Hp, w = sizeof(float) * (size_t)p.Hp;
+            cudaMemcpy2DAsync(g.lock_tail, 2 * w, g.mag + (size_t)(nf - 1) * p.Hp, pitch, w, g.rows, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpy2DAsync(g.lock_tail + p.Hp, 2 * w, g.phase + (size_t)(nf - 1) * p.Hp, pitch, w, g.rows, cudaMemcpyDeviceToDevice, st);
+            sp = span_begin(7, st); launch_lock_chain(p, g, nf, st); span_end(sp, st); ++launches;
         } else if (!d.vocoder && !d.constant_mode) {
             sp = span_begin(1, st); launch_phase_core(p, g, d.cfg.coremode, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches;
         }
@@ -344,6 +357,7 @@ struct Pipeline {
 // Device workspace for a group of rows.
 struct Workspace {
     DevBuf mag, phase, frames, prev_phase, prev_out, peaks, first, n_in, n_out;
+    DevBuf lock_hdr, lock_rec, lock_map, lock_csn, lock_tail, lock_kind, lock_rot;   // phase-locked core on Cartesian spectra
     int rows = 0, F = 0, Fr = 0;
 
     // halo: frames before the current chunk that the overlap-add of the chunk (and of the resampler history before
@@ -364,6 +378,16 @@ struct Workspace {
         CU(prev_out.ensure(sizeof(float) * (size_t)rows * p.half));
         CU(peaks.ensure(sizeof(int) * (size_t)streams * (1 + pl.max_peaks())));
         CU(first.ensure(sizeof(int) * (size_t)streams));
+        if (pl.cartesian() && pl.cartesian_lock()) {
+            const size_t slots = (size_t)rows * F, mp = (size_t)pl.max_peaks();
+            CU(lock_hdr.ensure(sizeof(int2) * slots));
+            CU(lock_rec.ensure(sizeof(float4) * slots * lock_rec_stride(p, (int)mp) + sizeof(float4) * 256));
+            CU(lock_map.ensure(sizeof(unsigned short) * slots * p.half));
+            CU(lock_csn.ensure(sizeof(float2) * slots * mp));
+            CU(lock_tail.ensure(sizeof(float) * (size_t)rows * 2 * p.Hp));
+            CU(lock_kind.ensure(sizeof(int) * (size_t)rows));
+            CU(lock_rot.ensure(sizeof(float) * (size_t)rows * mp));
+        }
         return PVGPU_OK;
     }
 
@@ -374,6 +398,10 @@ struct Workspace {
         CU(cudaMemsetAsync(prev_out.p, 0, sizeof(float) * (size_t)rows * p.half, st));
         CU(cudaMemsetAsync(peaks.p, 0, sizeof(int) * (size_t)streams * (1 + pl.max_peaks()), st));
         CU(cudaMemsetAsync(first.p, 0, sizeof(int) * (size_t)streams, st));
+        if (lock_kind.p) {
+            CU(cudaMemsetAsync(lock_kind.p, 0, sizeof(int) * (size_t)rows, st));
+            CU(cudaMemsetAsync(lock_rot.p, 0, sizeof(float) * (size_t)rows * pl.max_peaks(), st));
+        }
         return PVGPU_OK;
     }
 
@@ -382,6 +410,9 @@ struct Workspace {
         g.frames = frames.as<float>(); g.Fr = Fr;
         g.prev_phase = prev_phase.as<float>(); g.prev_out = prev_out.as<float>();
         g.peaks = peaks.as<int>(); g.maxpk = pl.max_peaks(); g.started = first.as<int>();
+        g.lock_hdr = lock_hdr.as<int2>(); g.lock_rec = lock_rec.as<float4>(); g.rec_stride = lock_rec_stride(pl.p, pl.max_peaks());
+        g.lock_map = lock_map.as<unsigned short>(); g.lock_csn = lock_csn.as<float2>(); g.lock_tail = lock_tail.as<float>();
+        g.lock_kind = lock_kind.as<int>(); g.lock_rot = lock_rot.as<float>();
     }
 };
 
@@ -453,7 +484,10 @@ struct pvgpu_batch {
     bool overlap_stages() const { return n_contexts > 1; }
     size_t max_ws_bytes = (size_t)24 << 30;   // largest workspace a single group may take
     size_t ws_bytes_per_row() const {
-        return sizeof(float) * ((size_t)4 * frames_per_chunk * pl.p.Hp + (size_t)(2 * frames_per_chunk + halo) * pl.p.N + 2 * (size_t)pl.p.half);
+        size_t b = sizeof(float) * ((size_t)4 * frames_per_chunk * pl.p.Hp + (size_t)(2 * frames_per_chunk + halo) * pl.p.N + 2 * (size_t)pl.p.half);
+        if (pl.cartesian() && pl.cartesian_lock())   // records, bin->region maps and rotations of k_lock_peaks / k_lock_chain
+            b += (size_t)frames_per_chunk * (16 * (size_t)lock_rec_stride(pl.p, pl.max_peaks()) + 2 * (size_t)pl.p.half + 8 * (size_t)pl.max_peaks() + 8);
+        return b;
     }
     int run_for_chunk = 0;   // frames_per_chunk the resampler work lists were built for
     int prepare_runs() {

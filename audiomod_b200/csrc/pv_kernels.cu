@@ -620,6 +620,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_phase_lock_t(const 
     if (tid == 0) { gpk[0] = nprev; g.started[stream] = (total > 0 || !first) ? 1 : 0; }
 }
 
+#include "pv_lock.cuh"   // k_lock_peaks / k_lock_chain: the phase-locked core on Cartesian spectra
+
 // coremode 2: phase *= phaseIncrement / hop (two float roundings, :558-572)
 __global__ void k_int_ratio(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base, long k0) {
     const int row = blockIdx.y, f = blockIdx.x;
@@ -732,6 +734,7 @@ struct SynthBinLoader {
     const float *__restrict__ gmag, *__restrict__ gph, *__restrict__ cmag, *__restrict__ cph;
     const float *__restrict__ wphase;   // whisper phases of this (slice, channel)
     int spec, kind;                     // DevRows::spec / DevRows::synth_kind
+
     // analysis magnitude of bin i (FFT.cc:2624); with Cartesian spectra it is formed here, with the same operations
     __device__ __forceinline__ float in_mag(int i) const {
         if (!spec) return gmag[i];
@@ -761,6 +764,7 @@ struct SynthBinLoader {
             m = in_mag(i); ph = wphase[i];
         } else if (kind == 3 && spec) { // constant mode: the spectrum goes back unchanged
             m = gmag[i]; ph = gph[i];
+
         } else if (p.freq_comp != 0.f) {  // freqCompSlice (:842-923) as a gather
             if (p.freq_comp > 1.0f || i < hs) {
                 const int src = __float2int_rn(__fmul_rn((float)i, p.freq_comp));
@@ -792,7 +796,7 @@ struct SynthBinLoader {
     __device__ __forceinline__ float2 operator()(int i) const { return finish(load(i)); }
 };
 
-template <int N>
+template <int N, bool kLock>   // kLock: Cartesian spectra of the phase-locked core only (g.synth_kind == 4), no other mode's code
 __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(const DevPlan p, const DevRows g, const float *__restrict__ car_mag,
                                                                                  const float *__restrict__ car_phase, long k0, int nf, int total) {
     constexpr int NC = N / 2;
@@ -806,7 +810,78 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
     const bool active = fid < total;
     const int row = active ? fid / nf : 0, f = active ? fid % nf : 0;
     const long k = k0 + f;
-    if (active) {
+    if (kLock && active) {
+        // Phase-locked core on Cartesian spectra: bin i of a locked frame is (re, im) * (cos, sin) of its region's rotation
+        // (pv_lock.cuh); first and classic frames, and the Nyquist bin, go back as they are.  1/N scale (:1024), then the
+        // inverse real-FFT pre-pass (kiss_fftr.c:123-159).  Four pairs per step: all their loads are issued before the
+        // dependent (cos, sin) gathers.
+        const int64_t slot = (int64_t)row * g.F + f;
+        const float *__restrict__ gre = g.mag + slot * p.Hp, *__restrict__ gim = g.phase + slot * p.Hp;
+        const bool locked = g.lock_hdr[slot].y == 2;
+        const unsigned short *__restrict__ lmap = g.lock_map + slot * p.half;
+        const float2 *__restrict__ lcsn = g.lock_csn + slot * g.maxpk;
+        const float2 *__restrict__ stw = p.stw_inv;
+        constexpr int Q = (NC / 2) / T;
+        constexpr int U = Q >= 4 ? 4 : Q;
+        const int sa = fft_pad(fft_slot_of_input<NC>(t)), sb = fft_pad(fft_slot_of_input<NC>((T - t) & (T - 1)));
+        const float inv_n = p.inv_n;
+#pragma unroll 1
+        for (int q0 = 0; q0 < Q; q0 += U) {
+            float2 lo[U], hi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int kk = t + T * (q0 + u);
+                lo[u] = make_float2(gre[kk], gim[kk]);
+                hi[u] = make_float2(gre[NC - kk], gim[NC - kk]);
+            }
+            if (locked) {
+                float2 cl[U], ch[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int kk = t + T * (q0 + u);
+                    cl[u] = lcsn[lmap[kk]];
+                    ch[u] = kk == 0 ? make_float2(1.f, 0.f) : lcsn[lmap[NC - kk]];   // bin NC (Nyquist) is not part of any region
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    lo[u] = make_float2(lo[u].x * cl[u].x - lo[u].y * cl[u].y, lo[u].x * cl[u].y + lo[u].y * cl[u].x);
+                    hi[u] = make_float2(hi[u].x * ch[u].x - hi[u].y * ch[u].y, hi[u].x * ch[u].y + hi[u].y * ch[u].x);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u, kk = t + T * q;
+                const float2 fk = make_float2(__fmul_rn(lo[u].x, inv_n), __fmul_rn(lo[u].y, inv_n));
+                const float2 fq = make_float2(__fmul_rn(hi[u].x, inv_n), __fmul_rn(hi[u].y, inv_n));
+                if (kk == 0) {
+                    buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk.x + fq.x, fk.x - fq.x);
+                } else {
+                    const float2 fnkc = make_float2(fq.x, -fq.y);
+                    const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
+                    const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
+                    const float2 a = cadd_rn(fek, fok);
+                    const float2 b = csub_rn(fek, fok);
+                    buf[sa + fft_pad(fft_slot_of_input<NC>(T * q))] = a;
+                    buf[sb + (t == 0 ? fft_pad(fft_slot_of_input<NC>((T * (16 - q)) & (NC - 1))) : fft_pad(fft_slot_of_input<NC>(T * (15 - q))))] =
+                        make_float2(b.x, -b.y);
+                }
+            }
+        }
+        if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)
+            float2 fk = make_float2(gre[NC / 2], gim[NC / 2]);
+            if (locked) {
+                const float2 cs = lcsn[lmap[NC / 2]];
+                fk = make_float2(fk.x * cs.x - fk.y * cs.y, fk.x * cs.y + fk.y * cs.x);
+            }
+            fk = make_float2(__fmul_rn(fk.x, inv_n), __fmul_rn(fk.y, inv_n));
+            const float2 fnkc = make_float2(fk.x, -fk.y);
+            const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
+            const float2 fok = cmul_rn(d, __ldg(&stw[NC / 2]));
+            const float2 b = csub_rn(fek, fok);
+            buf[fft_pad(fft_slot_of_input<NC>(NC / 2))] = make_float2(b.x, -b.y);
+        }
+    }
+    if (!kLock && active) {
         const int64_t so = ((int64_t)row * g.F + f) * p.Hp;
         const int64_t co = (int64_t)(k - g.aux_base) * p.Hp;
         const float *wph = g.whisper ? g.whisper + ((int64_t)(k - g.aux_base) * g.channels + row % g.channels) * p.H : nullptr;
@@ -1089,6 +1164,13 @@ cudaError_t configure_kernels() {
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<8, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+#define PV_LOCK_ATTR(CC) \
+    if ((e = cudaFuncSetAttribute(k_lock_peaks<4, 256, 4, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e; \
+    if ((e = cudaFuncSetAttribute(k_lock_peaks<4, 512, 2, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e; \
+    if ((e = cudaFuncSetAttribute(k_lock_peaks<8, 512, 2, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    PV_LOCK_ATTR(0) PV_LOCK_ATTR(1) PV_LOCK_ATTR(2)
+#undef PV_LOCK_ATTR
+    if ((e = cudaFuncSetAttribute(k_lock_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -1145,6 +1227,28 @@ void launch_phase_core(const DevPlan &p, const DevRows &g, int coremode, const S
     else k_phase_core<false><<<streams, threads, sm, st>>>(p, g, recs, recs_base, k0, nframes);
 }
 
+int lock_rec_stride(const DevPlan &p, int maxpk) { return maxpk > p.half / 2 ? maxpk : p.half / 2; }
+
+template <int kC>
+static void launch_lock_peaks_c(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
+    const int streams = g.rows / g.channels;
+    const size_t sm = lock_peaks_smem(p.half, g.channels, g.maxpk);
+    const dim3 grid((nframes + kLockRun - 1) / kLockRun, streams);
+    if (p.N == 8192) k_lock_peaks<8, 512, 2, kC><<<grid, p.half / 8, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+    else if (p.half / 4 > 256) k_lock_peaks<4, 512, 2, kC><<<grid, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+    else k_lock_peaks<4, 256, 4, kC><<<grid, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+}
+
+void launch_lock_peaks(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
+    if (g.channels == 1) launch_lock_peaks_c<1>(p, g, recs, recs_base, k0, nframes, st);
+    else if (g.channels == 2) launch_lock_peaks_c<2>(p, g, recs, recs_base, k0, nframes, st);
+    else launch_lock_peaks_c<0>(p, g, recs, recs_base, k0, nframes, st);
+}
+
+void launch_lock_chain(const DevPlan &p, const DevRows &g, int nframes, cudaStream_t st) {
+    k_lock_chain<<<g.rows / g.channels, kChainThreads, lock_chain_smem(p.half, g.channels, g.maxpk), st>>>(p, g, nframes);
+}
+
 void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table, long k0, int nframes, cudaStream_t st) {
     dim3 grid(nframes, g.rows);
     k_fixed_phase<<<grid, 256, 0, st>>>(p, g, table, k0);
@@ -1155,7 +1259,8 @@ static void launch_synthesise_t(const DevPlan &p, const DevRows &g, const float 
     using S = FftShape<N / 2>;
     constexpr int T = S::kThreads, G = (T >= 256) ? 1 : 256 / T;
     const int total = nframes * g.rows;
-    k_synthesise_t<N><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
+    if (g.synth_kind == 4) k_synthesise_t<N, true><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
+    else k_synthesise_t<N, false><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
 }
 
 void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase, long k0, int nframes, cudaStream_t st) {

@@ -51,15 +51,30 @@ struct DevRows {
     int *peaks;               // [streams][1 + maxpk]: count, then previous peak list (shared by a stream's channels)
     int maxpk;
     int *started;             // [streams] 0 until the first slice of the stream went through the core
+    // phase-locked core on Cartesian spectra (pv_lock.cuh): k_lock_peaks -> k_lock_chain -> k_synthesise_t
+    int2 *lock_hdr;           // [rows][F]: (peaks, frame kind: 0 pass-through first frame, 1 classic propagation, 2 locked)
+    float4 *lock_rec;         // [rows][F][rec_stride]: per peak (phi[p2], prev_phase[p1], advance, p1 | region of p1 << 16);
+    int rec_stride;           //   classic frames: float advance[half], prev_phase[half].  rec_stride = max(maxpk, half / 2)
+    unsigned short *lock_map; // [rows][F][half]: region (= peak index) of every bin of the frame
+    float2 *lock_csn;         // [rows][F][maxpk]: (cos, sin) of every region's rotation
+    float *lock_tail;         // [rows][2][Hp]: (re, im) of the last frame of the previous launch
+    int *lock_kind;           // [rows]: chain state of the channel (kind 0..3, see pv_lock.cuh)
+    float *lock_rot;          // [rows][maxpk]: rotations of the channel's previous frame (kind 2); kind 1 keeps prev_out
     long aux_base;            // slice index of element 0 of the whisper table / carrier spectra
     int spec;                 // 0: spectra are (mag, phase); 1: Cartesian (re in mag[], im in phase[]) -- modes that never use the
-                              //    analysis phase (robotic, whisper, vocoder, constant) skip sqrtf/atan2f in the analysis kernel
-    int synth_kind;           // 0: phases come from the spectra; 1: robotic (phase 0); 2: whisper (phase table); 3: constant
+                              //    analysis phase (robotic, whisper, vocoder, constant) and the phase-locked core of the plain
+                              //    shift / stretch modes (k_phase_lock_c) skip sqrtf/atan2f in the analysis kernel
+    int synth_kind;           // 0: phases come from the spectra; 1: robotic (phase 0); 2: whisper (phase table); 3: constant;
+                              // 4: Cartesian phase-locked core (rotate every bin by its region's (cos, sin))
     const float *whisper;     // [slices][channels][H] phases of the whisper mode (indexed by absolute slice - aux_base)
 };
 
 void launch_analyse(const DevPlan &p, const DevRows &g, long k0, int nframes, cudaStream_t st);
 void launch_phase_core(const DevPlan &p, const DevRows &g, int coremode, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st);
+// the phase-locked core on Cartesian spectra (g.spec == 1): frame-parallel part, then the serial chain
+void launch_lock_peaks(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st);
+void launch_lock_chain(const DevPlan &p, const DevRows &g, int nframes, cudaStream_t st);
+int lock_rec_stride(const DevPlan &p, int maxpk);
 void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table /*[slices][channels][H] indexed by absolute slice, or null = zeros*/,
                         long k0, int nframes, cudaStream_t st);
 void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase /*[slices][Hp] indexed by absolute slice, or null*/,

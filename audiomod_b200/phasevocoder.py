@@ -175,7 +175,7 @@ class PhaseVocoderBatch:
         self.run_host_rows(in_rows, out_rows, fmt)
         return outs
 
-    KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "ola_resample", "unused", "fixed_phase")
+    KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "ola_resample", "unused", "fixed_phase", "lock_peaks", "lock_chain")
 
     def profile(self, enable=True):
         check(_lib.lib().pvgpu_batch_profile(self._h, int(bool(enable))))
