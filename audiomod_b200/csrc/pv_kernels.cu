@@ -1038,24 +1038,42 @@ __global__ void __launch_bounds__(256, 5) k_ola_resample(const DevPlan p, const 
     const int64_t row_out = (int64_t)row * g.out_stride - g.out_base;
     const int first_run_slice = (int)(ka - kmin);
     {
-        int sl = 0;
-        for (int e = tid; e < span; e += blockDim.x) {
-            while (T.res_rel[sl + 1] <= e) ++sl;   // last table slice starting at or before e (dropped slices share an offset)
-            const int i = e - T.res_rel[sl];
-            const int trel = T.ola_rel[sl] + i;
-            const int j1 = (int)(kmin - jmin) + sl;
-            float acc = 0.f;
-#pragma unroll 4
-            for (int j = T.j0[sl]; j <= j1; ++j) {
-                const int off = trel - T.fr_off[j];
-                if (off < N) acc += fr[T.fr_pos[j] + off];
+        // One warp per (table slice, 128-sample chunk): the frames covering a slice and their offsets are the same for all of
+        // its samples, so the inner loop over the covering frames is warp-uniform and each lane just adds four strided loads.
+        const int lane = tid & 31;
+        const int nchunk = (max_in / run + 127) >> 7;   // >= ceil(longest slice / 128)
+        const int nitem = nsl * nchunk;
+        for (int item = tid >> 5; item < nitem; item += blockDim.x >> 5) {
+            const int sl = item / nchunk, eb0 = (item - sl * nchunk) << 7;
+            const int r0 = T.res_rel[sl];
+            const int e_lo = max(r0, 0) + eb0, e_hi = min(T.res_rel[sl + 1], span);   // dropped slices share an offset: empty
+            if (e_lo >= e_hi) continue;
+            const int rel0 = T.ola_rel[sl] - r0;      // OLA position (relative to ola_base) of normalised sample e is rel0 + e
+            const int jb = (int)(kmin - jmin) + sl;
+            const int e0 = e_lo + lane;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = T.j0[sl]; j <= jb; ++j) {   // in slice order = the reference's accumulator sequence
+                const int o = rel0 + e0 - T.fr_off[j];   // offset of sample e0 inside frame j (never negative)
+                const float *__restrict__ src = fr + (T.fr_pos[j] + o);
+                if (o - lane + 127 < N) {   // the whole chunk lies inside the frame
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[u] += src[32 * u];
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (o + 32 * u < N) acc[u] += src[32 * u];
+                }
             }
-            const float v = acc / nrm[trel];
-            if (p.rs_active) {
-                s_in[e] = v;
-            } else if (sl >= first_run_slice && i < T.n_store[sl]) {
-                // no resampling: the normalised sample is the output sample (n_write / n_out clip)
-                pcm_store(g.out, g.fmt, row_out + out_first + T.out_rel[sl] + i, v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + 32 * u;
+                if (e >= e_hi) break;
+                const float v = acc[u] / nrm[rel0 + e];
+                if (p.rs_active) {
+                    s_in[e] = v;
+                } else if (sl >= first_run_slice && e - r0 < T.n_store[sl]) {
+                    // no resampling: the normalised sample is the output sample (n_write / n_out clip)
+                    pcm_store(g.out, g.fmt, row_out + out_first + T.out_rel[sl] + (e - r0), v);
+                }
             }
         }
     }

@@ -179,6 +179,47 @@ def test_empty_and_tiny_streams(A, oracle):
         assert_parity(y, r, f"tiny[{i}]")
 
 
+@pytest.mark.parametrize("kw,sr,ch", [
+    (dict(semitones=7.0, mode=0, coremode=1, fftsize=2048), 44100, 1),
+    (dict(semitones=4.0, mode=0, coremode=1, fftsize=2048), 44100, 2),
+    (dict(timeratio=1.5, mode=5, coremode=1, fftsize=1024), 48000, 2),
+    (dict(semitones=-3.0, mode=0, coremode=0, fftsize=2048), 44100, 2),
+])
+def test_silence_gaps_match_oracle(A, oracle, kw, sr, ch):
+    """Digital silence makes frames without any spectral peak: the phase-locked core falls back to the classic per-bin
+    propagation (phasevocoderprocess.cc:617-636) and later links peaks to a state left by it.  Streams that start with
+    silence, contain gaps (in one channel only, too) and end in silence must still match the oracle; the chunk size is
+    odd so that the transitions also cross launch boundaries."""
+    n = int(0.9 * sr)
+    xs = []
+    for i in range(4):
+        x = make_input("x", sr, ch, 0.9, 900 + i)[:, :n].copy()
+        a, b = int((0.15 + 0.1 * i) * sr), int((0.35 + 0.12 * i) * sr)
+        if i == 0:
+            x[:, :a] = 0.0                    # leading silence: the pass-through first frame is all zeros
+        elif i == 1:
+            x[:, a:b] = 0.0                   # a gap in every channel
+        elif i == 2:
+            x[ch - 1, a:b] = 0.0              # a gap in the last channel only (peak lists are shared by the channels)
+            x[:, int(0.7 * sr):] = 0.0        # and a silent tail
+        else:
+            x[:, a:a + 3000] = 0.0            # a gap of about one window: only a few peak-free frames
+            x[0, b:b + 2048] = 0.0
+        xs.append(x)
+    ref = [oracle.run_offline(x, sr, **kw) for x in xs]
+    tr, st, mode, core, fft = ctor_args(kw)
+    b = A.PhaseVocoderBatch(len(xs), n, sr, ch, tr, st, mode, core, fft)
+    b.tune(frames_per_chunk=5)
+    ys = b.run(xs)
+    b.close()
+    for i, (y, r) in enumerate(zip(ys, ref)):
+        assert_parity(y, r, f"silence {kw}[{i}]")
+    pv = A.phasevocoder(sr, ch, tr, st, mode, core, fft)
+    y = _cli_protocol(pv, xs[1], sr, mode)
+    pv.close()
+    assert_parity(y, ref[1], f"silence {kw} stream")
+
+
 def test_batch_invariance_bitwise(A):
     """A stream's result does not depend on what else is in the batch nor on chunk / group tuning."""
     sr = 44100

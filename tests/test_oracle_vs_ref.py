@@ -55,6 +55,24 @@ def test_oracle_matches_live_reference(oracle, case):
     assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+@pytest.mark.parametrize("kw,sr,ch", [
+    (dict(semitones=7.0, mode=0, coremode=1, fftsize=2048), 44100, 1),
+    (dict(semitones=4.0, mode=0, coremode=1, fftsize=2048), 44100, 2),
+    (dict(timeratio=1.5, mode=5, coremode=0, fftsize=1024), 48000, 2),
+])
+def test_oracle_silence_matches_live_reference(oracle, kw, sr, ch):
+    """Frames without spectral peaks (digital silence) take the classic-propagation branch of the phase-locked core
+    (phasevocoderprocess.cc:617-636); pin the oracle's restatement of it against the reference itself."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    x = make_input("x", sr, ch, 0.8, 321)
+    x[:, :int(0.1 * sr)] = 0.0
+    x[:, int(0.3 * sr):int(0.45 * sr)] = 0.0
+    x[ch - 1, int(0.55 * sr):int(0.65 * sr)] = 0.0
+    a, b = oracle.run_offline(x, sr, **kw), oracle.run_ref(x, sr, **kw)
+    assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_block_size_independence(oracle):
     """Output does not depend on the block size as long as the ring never overflows."""
     from audiomod_b200.synth import synth
