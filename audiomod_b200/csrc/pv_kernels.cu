@@ -1182,13 +1182,9 @@ cudaError_t configure_kernels() {
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<8, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-#define PV_LOCK_ATTR(CC) \
-    if ((e = cudaFuncSetAttribute(k_lock_peaks<4, 256, 4, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e; \
-    if ((e = cudaFuncSetAttribute(k_lock_peaks<4, 512, 2, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e; \
-    if ((e = cudaFuncSetAttribute(k_lock_peaks<8, 512, 2, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    PV_LOCK_ATTR(0) PV_LOCK_ATTR(1) PV_LOCK_ATTR(2)
-#undef PV_LOCK_ATTR
-    if ((e = cudaFuncSetAttribute(k_lock_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_lock_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_lock_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_lock_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_core<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     return cudaSuccess;
@@ -1247,24 +1243,37 @@ void launch_phase_core(const DevPlan &p, const DevRows &g, int coremode, const S
 
 int lock_rec_stride(const DevPlan &p, int maxpk) { return maxpk > p.half / 2 ? maxpk : p.half / 2; }
 
-template <int kC>
-static void launch_lock_peaks_c(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
-    const int streams = g.rows / g.channels;
-    const size_t sm = lock_peaks_smem(p.half, g.channels, g.maxpk);
-    const dim3 grid((nframes + kLockRun - 1) / kLockRun, streams);
-    if (p.N == 8192) k_lock_peaks<8, 512, 2, kC><<<grid, p.half / 8, sm, st>>>(p, g, recs, recs_base, k0, nframes);
-    else if (p.half / 4 > 256) k_lock_peaks<4, 512, 2, kC><<<grid, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
-    else k_lock_peaks<4, 256, 4, kC><<<grid, p.half / 4, sm, st>>>(p, g, recs, recs_base, k0, nframes);
+template <int N, int kC>
+static void launch_lock_peaks_nc(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
+    static bool configured = false;   // > 48 KB of dynamic shared memory for the larger sizes
+    if (!configured) { cudaFuncSetAttribute(k_lock_peaks<N, kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); configured = true; }
+    const dim3 grid((nframes + kLockRun - 1) / kLockRun, g.rows / g.channels);
+    k_lock_peaks<N, kC><<<grid, LockShape<N>::kThreads, lock_peaks_smem(p.half, g.channels, g.maxpk), st>>>(p, g, recs, recs_base, k0, nframes);
+}
+
+template <int N>
+static void launch_lock_peaks_n(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
+    if (g.channels == 1) launch_lock_peaks_nc<N, 1>(p, g, recs, recs_base, k0, nframes, st);
+    else if (g.channels == 2) launch_lock_peaks_nc<N, 2>(p, g, recs, recs_base, k0, nframes, st);
+    else launch_lock_peaks_nc<N, 0>(p, g, recs, recs_base, k0, nframes, st);
 }
 
 void launch_lock_peaks(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
-    if (g.channels == 1) launch_lock_peaks_c<1>(p, g, recs, recs_base, k0, nframes, st);
-    else if (g.channels == 2) launch_lock_peaks_c<2>(p, g, recs, recs_base, k0, nframes, st);
-    else launch_lock_peaks_c<0>(p, g, recs, recs_base, k0, nframes, st);
+    switch (p.N) {   // g.spec is only set for these sizes (Pipeline::cartesian)
+        case 512: return launch_lock_peaks_n<512>(p, g, recs, recs_base, k0, nframes, st);
+        case 1024: return launch_lock_peaks_n<1024>(p, g, recs, recs_base, k0, nframes, st);
+        case 2048: return launch_lock_peaks_n<2048>(p, g, recs, recs_base, k0, nframes, st);
+        case 4096: return launch_lock_peaks_n<4096>(p, g, recs, recs_base, k0, nframes, st);
+        default: return launch_lock_peaks_n<8192>(p, g, recs, recs_base, k0, nframes, st);
+    }
 }
 
 void launch_lock_chain(const DevPlan &p, const DevRows &g, int nframes, cudaStream_t st) {
-    k_lock_chain<<<g.rows / g.channels, kChainThreads, lock_chain_smem(p.half, g.channels, g.maxpk), st>>>(p, g, nframes);
+    const int streams = g.rows / g.channels;
+    const size_t sm = lock_chain_smem(p.half, g.channels, g.maxpk);
+    if (g.channels == 1) k_lock_chain<1><<<streams, kChainThreads, sm, st>>>(p, g, nframes);
+    else if (g.channels == 2) k_lock_chain<2><<<streams, kChainThreads, sm, st>>>(p, g, nframes);
+    else k_lock_chain<0><<<streams, kChainThreads, sm, st>>>(p, g, nframes);
 }
 
 void launch_fixed_phase(const DevPlan &p, const DevRows &g, const float *table, long k0, int nframes, cudaStream_t st) {

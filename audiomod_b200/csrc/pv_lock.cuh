@@ -49,12 +49,22 @@ inline size_t lock_peaks_smem(int half, int C, int maxpk) {
 }
 inline size_t lock_chain_smem(int half, int C, int maxpk) { return sizeof(float) * ((size_t)C * 2 * maxpk + (size_t)C * half) + sizeof(int) * 2 * (size_t)C; }
 
-template <int E, int kMaxThreads, int kMinBlocks, int kC>   // kC: channels per stream when 1 or 2, 0 = any (run time)
-__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_lock_peaks(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, long recs_base,
-                                                                        long k0, int nframes) {
-    static_assert(E == 4 || E == 8, "bins per thread");
+// launch shape of k_lock_peaks<N, kC>: E bins per thread, half / E threads, CTAs per SM the register budget allows
+template <int N> struct LockShape {
+    static constexpr int kHalf = N / 2;
+    static constexpr int E = N == 8192 ? 8 : 4;
+    static constexpr int kThreads = kHalf / E;
+    static constexpr int kMinBlocks = 1024 / kThreads > 16 ? 16 : 1024 / kThreads;   // 64 registers per thread
+    static constexpr int kMaxPk = kHalf / 3 + 2;   // == Pipeline::max_peaks(): peaks are at least 3 bins apart
+};
+
+template <int N, int kC>   // kC: channels per stream when 1 or 2, 0 = any (run time)
+__global__ void __launch_bounds__(LockShape<N>::kThreads, LockShape<N>::kMinBlocks) k_lock_peaks(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs,
+                                                                                                   long recs_base, long k0, int nframes) {
+    constexpr int E = LockShape<N>::E;
     extern __shared__ float smem[];
-    const int half = p.half, C = kC ? kC : g.channels, maxpk = g.maxpk;
+    constexpr int half = LockShape<N>::kHalf, maxpk = LockShape<N>::kMaxPk, nthr = LockShape<N>::kThreads, nwarp = nthr / 32;
+    const int C = kC ? kC : g.channels;
     float *s_q = smem;                                // half + 8   squared magnitudes, two guard bins each side
     float *s_cre = s_q + half + 8;                    // half       current frame
     float *s_cim = s_cre + half;                      // half
@@ -65,8 +75,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_lock_peaks(const De
     int *s_start = s_pk1 + maxpk;                     // maxpk + 1  region starts of the current frame
     int *s_wsum = s_start + maxpk + 1;                // 32
     unsigned short *s_map = (unsigned short *)(smem + lock_peaks_map_offset(half, C, maxpk));   // C * half   region of every bin in the channel's latest frame
-    const int stream = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int stream = blockIdx.y, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int b0 = tid * E;
     const int fa = blockIdx.x * kLockRun, fb = min(fa + kLockRun, nframes);
     const int f_first = (k0 + fa > 0) ? fa - 1 : fa;   // a frame before the run exists: warm up on it (peaks, regions, spectrum)
@@ -78,16 +88,21 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_lock_peaks(const De
     float pre[E], pim[E];
     int ff = f_first, cf = 0;
     const int64_t row0 = (int64_t)stream * C;
+    const int64_t ch_step = (int64_t)g.F * p.Hp;                 // next channel, same frame
+    const int64_t fr_step = (int64_t)p.Hp - (C - 1) * ch_step;   // channel C-1 of frame f -> channel 0 of frame f+1
+    const float *fre = g.mag + (row0 * g.F + max(f_first, 0)) * p.Hp + b0;   // (frame max(f_first, 0), channel 0, bin b0)
+    const float *fim = g.phase + (row0 * g.F + max(f_first, 0)) * p.Hp + b0;
     auto fetch = [&]() {
         const float *sr, *si;
         if (ff < 0) {
             sr = g.lock_tail + (row0 + cf) * 2 * p.Hp + b0;
             si = sr + p.Hp;
         } else {
-            const int64_t off = ((row0 + cf) * g.F + ff) * p.Hp + b0;
-            sr = g.mag + off; si = g.phase + off;
+            sr = fre; si = fim;
+            const int64_t step = (kC == 1 || cf == C - 1) ? fr_step : ch_step;
+            fre += step; fim += step;
         }
-        if (++cf == C) { cf = 0; ++ff; }
+        if (kC == 1 || ++cf == C) { cf = 0; ++ff; }
 #pragma unroll
         for (int e = 0; e < E; e += 4) {
             const float4 r4 = *(const float4 *)(sr + e);
@@ -150,7 +165,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_lock_peaks(const De
             // peaks in the warps before this one, and in the whole frame: a second scan over the (at most 16) warp totals
             int ws = lane < nwarp ? s_wsum[lane] : 0;
 #pragma unroll
-            for (int d = 1; d < 16; d <<= 1) {
+            for (int d = 1; d < nwarp; d <<= 1) {
                 const int v = __shfl_up_sync(0xffffffffu, ws, d);
                 if (lane >= d) ws += v;
             }
@@ -282,9 +297,10 @@ __device__ __noinline__ void lock_chain_classic(int half, const float *__restric
 }
 
 constexpr int kChainThreads = 128;
+template <int kC>   // channels per stream when 1 or 2, 0 = any (run time)
 __global__ void __launch_bounds__(kChainThreads, 10) k_lock_chain(const DevPlan p, const DevRows g, int nframes) {
     extern __shared__ float smem[];
-    const int half = p.half, C = g.channels, maxpk = g.maxpk;
+    const int half = p.half, C = kC ? kC : g.channels, maxpk = g.maxpk;
     float *s_rot = smem;                          // C * 2 * maxpk   rotation of every region of the channel's previous frame (ping-pong)
     float *s_out = s_rot + C * 2 * maxpk;         // C * half        prev_outphase while the channel is in state kind 1
     int *s_kind = (int *)(s_out + C * half);      // C
@@ -300,38 +316,50 @@ __global__ void __launch_bounds__(kChainThreads, 10) k_lock_chain(const DevPlan 
         if (tid == 0) { s_kind[c] = kd; s_flip[c] = 0; }
     }
     __syncthreads();
-    // the header and this thread's first two records of the next (frame, channel) are fetched one iteration ahead; the
-    // record area is padded by 2 * kChainThreads entries, so the loads are unconditional (garbage beyond the frame's peaks)
+    int kind_r[kC ? kC : 1], flip_r[kC ? kC : 1];
+#pragma unroll
+    for (int c = 0; c < kC; ++c) { kind_r[c] = s_kind[c]; flip_r[c] = 0; }
+    // Running pointers to (frame, channel) of the next fetch and of the current iteration.  The header and this thread's
+    // first two records of the next (frame, channel) are fetched one iteration ahead; the record area is padded by
+    // 2 * kChainThreads entries, so the loads are unconditional (garbage beyond the frame's peaks, never used).
     const int rs = g.rec_stride;
-    const int2 *__restrict__ hdr_p = g.lock_hdr + row0 * g.F;            // (channel 0, frame 0)
-    const float4 *__restrict__ rec_p = g.lock_rec + row0 * g.F * rs + tid;
+    const int64_t ch_step = g.F, fr_step = 1 - (int64_t)(C - 1) * g.F;   // in (row, frame) slots
+    const int2 *__restrict__ hdr_f = g.lock_hdr + row0 * g.F;
+    const float4 *__restrict__ rec_f = g.lock_rec + row0 * g.F * rs + tid;
+    const float4 *__restrict__ rec_c = rec_f;
+    float2 *__restrict__ csn_c = g.lock_csn + row0 * g.F * maxpk;
     int2 hdr_n = make_int2(0, 0);
     float4 rec_n0 = make_float4(0.f, 0.f, 0.f, 0.f), rec_n1 = rec_n0;
-    int ff = 0, cf = 0;
+    int cf = 0, left = nframes * C;   // iterations still to fetch
     auto fetch = [&]() {
-        const int64_t sl = (int64_t)cf * g.F + ff;
-        hdr_n = hdr_p[sl];
-        rec_n0 = rec_p[sl * rs];
-        rec_n1 = rec_p[sl * rs + nthr];
-        if (++cf == C) { cf = 0; ++ff; }
+        hdr_n = *hdr_f;
+        rec_n0 = rec_f[0];
+        rec_n1 = rec_f[nthr];
+        const int64_t step = (kC == 1 || cf == C - 1) ? fr_step : ch_step;
+        if (kC != 1) cf = cf == C - 1 ? 0 : cf + 1;
+        hdr_f += step; rec_f += step * rs;
+        --left;
     };
-    if (nframes > 0) fetch();
+    if (left > 0) fetch();
     for (int f = 0; f < nframes; ++f) {
+#pragma unroll
         for (int c = 0; c < C; ++c) {
             const int2 hdr = hdr_n;
             const float4 rec0 = rec_n0, rec1 = rec_n1;
-            if (ff < nframes) fetch();
-            const int kp = s_kind[c], fl = s_flip[c];
+            if (left > 0) fetch();
+            // The channel's state (kind, ping-pong side) is replaced at the end of the iteration; with 1 or 2 channels every
+            // thread keeps its own copy in registers, otherwise all threads must have read it before thread 0 replaces it.
+            int kp, fl;
+            if (kC) { kp = kind_r[c]; fl = flip_r[c]; }
+            else { kp = s_kind[c]; fl = s_flip[c]; __syncthreads(); }
             const float *rot_p = s_rot + (c * 2 + fl) * maxpk;
             float *rot_n = s_rot + (c * 2 + (fl ^ 1)) * maxpk;
             float *out_c = s_out + c * half;
             int new_kind;
             if (hdr.y == 2) {
                 const int npk = hdr.x;
-                const int64_t slot = (row0 + c) * g.F + f;
-                float2 *__restrict__ csn = g.lock_csn + slot * maxpk;
                 for (int r = tid; r < npk; r += nthr) {
-                    const float4 rec = r == tid ? rec0 : r == tid + nthr ? rec1 : g.lock_rec[slot * rs + r];
+                    const float4 rec = r == tid ? rec0 : r == tid + nthr ? rec1 : rec_c[r - tid];
                     const float php = rec.x, a = rec.y, adv = rec.z;
                     const int link = __float_as_int(rec.w);
                     float po;   // prev_outphase[p1]
@@ -344,7 +372,7 @@ __global__ void __launch_bounds__(kChainThreads, 10) k_lock_chain(const DevPlan 
                     rot_n[r] = rot;
                     float sn, cs;
                     sincosf(rot, &sn, &cs);
-                    csn[r] = make_float2(cs, sn);
+                    csn_c[r] = make_float2(cs, sn);
                 }
                 new_kind = 2;
             } else if (hdr.y == 0) {
@@ -354,10 +382,18 @@ __global__ void __launch_bounds__(kChainThreads, 10) k_lock_chain(const DevPlan 
                 lock_chain_classic(half, (const float *)(g.lock_rec + slot * rs), g.lock_map + slot * half, g.mag + slot * p.Hp, g.phase + slot * p.Hp, kp, rot_p, out_c);
                 new_kind = 1;
             }
-            if (tid == 0) { s_kind[c] = new_kind; if (new_kind == 2) s_flip[c] = fl ^ 1; }
+            if (kC) { kind_r[c] = new_kind; if (new_kind == 2) flip_r[c] = fl ^ 1; }
+            else if (tid == 0) { s_kind[c] = new_kind; if (new_kind == 2) s_flip[c] = fl ^ 1; }
+            const int64_t step = (kC == 1 || c == C - 1) ? fr_step : ch_step;
+            rec_c += step * rs; csn_c += step * maxpk;
             __syncthreads();
         }
     }
+    if (kC && tid == 0) {
+#pragma unroll
+        for (int c = 0; c < kC; ++c) { s_kind[c] = kind_r[c]; s_flip[c] = flip_r[c]; }
+    }
+    __syncthreads();
     for (int c = 0; c < C; ++c) {
         const int64_t row = row0 + c;
         const int kd = s_kind[c];
