@@ -977,17 +977,23 @@ struct OlaTables {
     int fr_pos[kOlaMaxFrames];            // slot * N of that frame in the ring
 };
 
-template <int OV>   // sinc-table oversampling of the interpolated resampler mode; 0 = direct table or no resampler
-__global__ void __launch_bounds__(256, 5) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
+struct NoQuadTab { int unused; };
+// OV: sinc-table oversampling of the interpolated resampler mode; 0 = direct table or no resampler.
+// Tab: QuadTab = the quad table is the kernel parameter qt (constant bank), NoQuadTab = it is staged in shared memory.
+template <int OV, class Tab>
+__global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
                                                       int64_t norm_base, long recs_base, long k0, int nf, int run, int max_in, const ResampleRun *__restrict__ runs,
-                                                      const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, long run_origin) {
+                                                      const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, long run_origin,
+                                                      const __grid_constant__ Tab qt) {
+    constexpr bool kParamTab = sizeof(Tab) > sizeof(NoQuadTab);
     extern __shared__ float4 smem4[];
     __shared__ OlaTables T;
+    __shared__ ResampleRun s_hdr;
     const int row = blockIdx.y;
     const long ka = k0 + (long)blockIdx.x * run;
     const long kb = min(ka + run, k0 + (long)nf);
     const int L = p.rs_active ? (int)p.rs_filt_len : 1;
-    const bool quad = p.rs_active && !p.rs_direct;
+    const bool quad = p.rs_active && !p.rs_direct && !kParamTab;   // quads staged in shared memory
     float4 *s_quad = smem4;
     // s_in[-L .. 0) stays zero: the resampler's history before the start of a stream (speex mem is zero-initialised)
     float *s_in = (float *)(smem4 + (quad ? p.rs_table_len : 0)) + (p.rs_active ? L : 0);
@@ -1026,6 +1032,8 @@ __global__ void __launch_bounds__(256, 5) k_ola_resample(const DevPlan p, const 
         T.fr_off[i] = (int)(rr[j].ola_off - ola_base);
         T.fr_pos[i] = (int)(j % g.Fr) * N;
     }
+    if (p.rs_active && tid < (int)(sizeof(ResampleRun) / sizeof(int)))   // this run's work-list header, needed after the overlap-add
+        ((int *)&s_hdr)[tid] = ((const int *)&runs[(ka - run_origin) / run])[tid];
     if (quad) {
         const float4 *__restrict__ tab4 = p.rs_quads;   // host-built (tab[e-2], tab[e-1], tab[e], tab[e+1])
         for (int e = tid; e < p.rs_table_len; e += blockDim.x) s_quad[e] = __ldg(&tab4[e]);
@@ -1052,16 +1060,22 @@ __global__ void __launch_bounds__(256, 5) k_ola_resample(const DevPlan p, const 
             const int jb = (int)(kmin - jmin) + sl;
             const int e0 = e_lo + lane;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int j = T.j0[sl]; j <= jb; ++j) {   // in slice order = the reference's accumulator sequence
-                const int o = rel0 + e0 - T.fr_off[j];   // offset of sample e0 inside frame j (never negative)
-                const float *__restrict__ src = fr + (T.fr_pos[j] + o);
-                if (o - lane + 127 < N) {   // the whole chunk lies inside the frame
+            // frames in slice order = the reference's accumulator sequence; four frames' loads are issued together
+            for (int j = T.j0[sl]; j <= jb; j += 4) {
+                float v[4][4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) acc[u] += src[32 * u];
-                } else {
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int jc = min(j + jj, jb);
+                    const int o = rel0 + e0 - T.fr_off[jc];   // offset of sample e0 inside the frame (never negative)
+                    const float *__restrict__ src = fr + (T.fr_pos[jc] + o);
+                    const int lim = j + jj <= jb ? N : 0;     // frames past the last one contribute nothing
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (o + 32 * u < N) acc[u] += src[32 * u];
+                    for (int u = 0; u < 4; ++u) v[jj][u] = o + 32 * u < lim ? src[32 * u] : 0.f;
                 }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[u] += v[jj][u];
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -1085,7 +1099,7 @@ __global__ void __launch_bounds__(256, 5) k_ola_resample(const DevPlan p, const 
     // inside a bucket and with buckets starting at multiples of 32 (ResampleRun, pv_kernels.cuh).  A warp therefore
     // works on one phase: the sinc quad of every tap is a single broadcast shared-memory access, and the lanes' input
     // windows are a constant few samples apart (bank-conflict free).
-    const ResampleRun hdr = runs[(ka - run_origin) / run];
+    const ResampleRun &hdr = s_hdr;   // fetched into shared memory at the start of the kernel
     constexpr int nb = OV > 0 ? OV : 1;
     const unsigned *__restrict__ ent_tab = rs_ent + hdr.ent_off;
     const float *__restrict__ frac_tab = rs_frac + hdr.ent_off;
@@ -1120,23 +1134,44 @@ __global__ void __launch_bounds__(256, 5) k_ola_resample(const DevPlan p, const 
                 pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), sum);
             }
         } else {
-            const float4 *q = s_quad + 4 + OV - bucket;
+            const int qoff = 4 + OV - bucket;
+            auto quad_at = [&](int tap) -> float4 {
+                if constexpr (kParamTab) return qt.q[qoff + tap * OV];
+                else return s_quad[qoff + tap * OV];
+            };
             float acc[kResPerThread][4];
 #pragma unroll
             for (int u = 0; u < kResPerThread; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
-            for (int j = 0; j < L; j += 4) {   // filt_len is a multiple of 4 (resample.c:712)
+            // two taps per stage, two stages in flight: the loads of the next stage are issued before the 32 FMAs of the
+            // current one (filt_len is a multiple of 4, resample.c:712)
+            float4 tqa[2], tqb[2];
+            float xa[2][kResPerThread], xb[2][kResPerThread];
+            auto load2 = [&](int j, float4 (&tq)[2], float (&x)[2][kResPerThread]) {
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const float4 tq = q[(j + jj) * OV];
+                for (int jj = 0; jj < 2; ++jj) {
+                    tq[jj] = quad_at(j + jj);
+#pragma unroll
+                    for (int u = 0; u < kResPerThread; ++u) x[jj][u] = xs[u][j + jj];
+                }
+            };
+            auto fma2 = [&](const float4 (&tq)[2], const float (&x)[2][kResPerThread]) {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
                     for (int u = 0; u < kResPerThread; ++u) {
-                        const float v = xs[u][j + jj];
-                        acc[u][0] += v * tq.x;
-                        acc[u][1] += v * tq.y;
-                        acc[u][2] += v * tq.z;
-                        acc[u][3] += v * tq.w;
+                        acc[u][0] += x[jj][u] * tq[jj].x;
+                        acc[u][1] += x[jj][u] * tq[jj].y;
+                        acc[u][2] += x[jj][u] * tq[jj].z;
+                        acc[u][3] += x[jj][u] * tq[jj].w;
                     }
-                }
+            };
+            load2(0, tqa, xa);
+#pragma unroll 1
+            for (int j = 0; j < L; j += 4) {
+                load2(j + 2, tqb, xb);
+                fma2(tqa, xa);
+                if (j + 4 < L) load2(j + 4, tqa, xa);
+                fma2(tqb, xb);
             }
 #pragma unroll
             for (int u = 0; u < kResPerThread; ++u) {
@@ -1174,11 +1209,15 @@ cudaError_t configure_kernels() {
     const int big = 200 * 1024;
     if ((e = cudaFuncSetAttribute(k_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_synthesise, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<0, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<1, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<1, QuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<2, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<2, QuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<4, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<4, QuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<8, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<8, QuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<8, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
@@ -1314,18 +1353,22 @@ int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out) {
 
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
                          long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
-                         long run_origin, cudaStream_t st) {
+                         long run_origin, const QuadTab *quads, cudaStream_t st) {
     const int L = p.rs_active ? (int)p.rs_filt_len : 1;
     const bool quad = p.rs_active && !p.rs_direct;
+    const bool param_tab = quad && quads != nullptr && p.rs_table_len <= kQuadParamMax;
     const int max_in = ((run * max_consumed + L + 8) + 3) & ~3;
-    const size_t sm = (quad ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)(max_in + (p.rs_active ? L : 0));
+    const size_t sm = (quad && !param_tab ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)(max_in + (p.rs_active ? L : 0));
     dim3 grid((nframes + run - 1) / run, g.rows);
-#define PV_OLA(OVV) k_ola_resample<OVV><<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, run_origin)
-    if (!quad) PV_OLA(0);
-    else if (p.rs_oversample == 8) PV_OLA(8);
-    else if (p.rs_oversample == 4) PV_OLA(4);
-    else if (p.rs_oversample == 2) PV_OLA(2);
-    else PV_OLA(1);
+    const NoQuadTab none{};
+#define PV_OLA(OVV, TAB, ARG) k_ola_resample<OVV, TAB><<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, run_origin, ARG)
+#define PV_OLA2(OVV) do { if (param_tab) PV_OLA(OVV, QuadTab, *quads); else PV_OLA(OVV, NoQuadTab, none); } while (0)
+    if (!quad) PV_OLA(0, NoQuadTab, none);
+    else if (p.rs_oversample == 8) PV_OLA2(8);
+    else if (p.rs_oversample == 4) PV_OLA2(4);
+    else if (p.rs_oversample == 2) PV_OLA2(2);
+    else PV_OLA2(1);
+#undef PV_OLA2
 #undef PV_OLA
 }
 

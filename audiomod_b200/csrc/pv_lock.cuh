@@ -31,7 +31,7 @@
 // area and the chain kernel rewrites their spectrum in place as mag * (cos, sin)(outphase).
 #pragma once
 
-constexpr int kLockRun = 16;   // frames per CTA of k_lock_peaks (plus one warm-up frame that is only peak-picked)
+constexpr int kLockRun = 32;   // frames per CTA of k_lock_peaks (plus one warm-up frame that is only peak-picked)
 
 // strict "mag[b] > every neighbour" (:589-592) decided on squared magnitudes q = fl(fl(re^2) + fl(im^2)): sqrtf is monotone,
 // so q_b <= q_n means "not greater"; q_b > q_n (1 + 2^-21) means the rounded square roots differ; in between the exactly

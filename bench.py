@@ -321,6 +321,13 @@ def main():
     per_frame = {"analyse": 4 * (hop + 2 * H), "phase_core": 4 * (2 * H + half), "synthesise": 4 * (2 * H + N),
                  "ola_resample": 4 * (N + shift / info["pitch_scale"])}
     per_frame["fixed_phase"] = 4 * H
+    # phase-locked core on Cartesian spectra (pv_lock.cuh): P peaks per frame is data dependent; a noise-like spectrum has a
+    # strict +-2 local maximum at one bin in five, which is what the synthetic workload measures (profiles/traffic.json)
+    P = half / 5.0
+    per_frame["lock_peaks"] = 4 * 2 * H * (1 + 1.0 / 32) + 16 * P + 2 * half + 8   # spectrum (+ warm-up frame per run) -> records, map, header
+    per_frame["lock_chain"] = 16 * P + 8 + 8 * P                                  # records, header -> (cos, sin) per region
+    if ktimes.get("lock_chain", (0, 0))[1] > 0:
+        per_frame["synthesise"] = 4 * (2 * H + N) + 2 * half + 8 * P + 8          # + bin->region map, rotations, header
     dom = max((k for k in per_frame if ktimes.get(k, (0, 0))[1] > 0), key=lambda k: ktimes[k][0])
     dom_ms, dom_launches = ktimes[dom]
     bytes_total = per_frame[dom] * slices * S * args.steps
