@@ -220,6 +220,31 @@ def test_silence_gaps_match_oracle(A, oracle, kw, sr, ch):
     assert_parity(y, ref[1], f"silence {kw} stream")
 
 
+@pytest.mark.parametrize("kw", [
+    dict(semitones=4.0, mode=0, coremode=1, fftsize=1024),
+    dict(timeratio=1.3, mode=5, coremode=1, fftsize=2048),
+    dict(semitones=-2.0, mode=2, coremode=1, fftsize=2048),
+])
+def test_three_channels(A, oracle, kw):
+    """More than two channels: the peak lists are still shared by all channels of a stream in processing order
+    (phasevocoderimpl.h:237-238); the kernels' run-time channel-count variants must follow it."""
+    sr, ch = 44100, 3
+    xs = [make_input("x", sr, ch, 0.5 - 0.1 * i, 700 + i) for i in range(2)]
+    xs[1][1, 4000:9000] = 0.0   # a silent stretch in the middle channel only
+    ref = [oracle.run_offline(x, sr, **kw) for x in xs]
+    tr, st, mode, core, fft = ctor_args(kw)
+    b = A.PhaseVocoderBatch(2, xs[0].shape[1], sr, ch, tr, st, mode, core, fft)
+    b.tune(frames_per_chunk=9)
+    ys = b.run(xs)
+    b.close()
+    for i, (y, r) in enumerate(zip(ys, ref)):
+        assert_parity(y, r, f"3ch {kw}[{i}]")
+    pv = A.phasevocoder(sr, ch, tr, st, mode, core, fft)
+    y = _cli_protocol(pv, xs[0], sr, mode)
+    pv.close()
+    assert_parity(y, ref[0], f"3ch {kw} stream")
+
+
 def test_batch_invariance_bitwise(A):
     """A stream's result does not depend on what else is in the batch nor on chunk / group tuning."""
     sr = 44100
