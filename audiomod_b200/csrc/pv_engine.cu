@@ -93,7 +93,6 @@ struct Pipeline {
     DevPlan p{};
     int device = 0;
     DevBuf b_window, b_twf, b_twi, b_stwf, b_stwi, b_perm, b_omega, b_rstab, b_rsquad;
-    std::unique_ptr<QuadTab> h_quads;   // host copy of the quad table when it fits a kernel parameter
     // schedule on the device
     DevBuf b_recs, b_norm, b_whisper, b_carmag, b_carph;
     long recs_base = 0, recs_count = 0;
@@ -189,10 +188,6 @@ struct Pipeline {
                 quads[4 * e + 3] = e + 1 < n ? tab[e + 1] : 0.f;
             }
             if ((rc = upload(b_rsquad, quads.data(), sizeof(float) * quads.size()))) return rc;
-            if (n <= kQuadParamMax) {   // small enough to travel as a kernel parameter (constant bank)
-                h_quads.reset(new QuadTab());
-                std::memcpy(h_quads->q, quads.data(), sizeof(float) * quads.size());
-            }
         }
         p.rs_quads = b_rsquad.as<float4>();
         return PVGPU_OK;
@@ -349,7 +344,7 @@ struct Pipeline {
         const SliceRec *recs = b_recs.as<SliceRec>();
         Span *sp = span_begin(3, st);
         launch_ola_resample(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, table_run, max_consumed, b_runs.as<ResampleRun>(),
-                            b_rsent.as<unsigned>(), b_rsfrac.as<float>(), run_origin, h_quads.get(), st);
+                            b_rsent.as<unsigned>(), b_rsfrac.as<float>(), run_origin, st);
         span_end(sp, st); ++launches;
     }
     void run_frames(const DevRows &g, long k0, int nf, cudaStream_t st) {

@@ -977,15 +977,10 @@ struct OlaTables {
     int fr_pos[kOlaMaxFrames];            // slot * N of that frame in the ring
 };
 
-struct NoQuadTab { int unused; };
-// OV: sinc-table oversampling of the interpolated resampler mode; 0 = direct table or no resampler.
-// Tab: QuadTab = the quad table is the kernel parameter qt (constant bank), NoQuadTab = it is staged in shared memory.
-template <int OV, class Tab>
+template <int OV>   // sinc-table oversampling of the interpolated resampler mode; 0 = direct table or no resampler
 __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
                                                       int64_t norm_base, long recs_base, long k0, int nf, int run, int max_in, const ResampleRun *__restrict__ runs,
-                                                      const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, long run_origin,
-                                                      const __grid_constant__ Tab qt) {
-    constexpr bool kParamTab = sizeof(Tab) > sizeof(NoQuadTab);
+                                                      const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, long run_origin) {
     extern __shared__ float4 smem4[];
     __shared__ OlaTables T;
     __shared__ ResampleRun s_hdr;
@@ -993,7 +988,7 @@ __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const 
     const long ka = k0 + (long)blockIdx.x * run;
     const long kb = min(ka + run, k0 + (long)nf);
     const int L = p.rs_active ? (int)p.rs_filt_len : 1;
-    const bool quad = p.rs_active && !p.rs_direct && !kParamTab;   // quads staged in shared memory
+    const bool quad = p.rs_active && !p.rs_direct;
     float4 *s_quad = smem4;
     // s_in[-L .. 0) stays zero: the resampler's history before the start of a stream (speex mem is zero-initialised)
     float *s_in = (float *)(smem4 + (quad ? p.rs_table_len : 0)) + (p.rs_active ? L : 0);
@@ -1135,10 +1130,7 @@ __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const 
             }
         } else {
             const int qoff = 4 + OV - bucket;
-            auto quad_at = [&](int tap) -> float4 {
-                if constexpr (kParamTab) return qt.q[qoff + tap * OV];
-                else return s_quad[qoff + tap * OV];
-            };
+            auto quad_at = [&](int tap) -> float4 { return s_quad[qoff + tap * OV]; };   // warp-uniform: a broadcast load
             float acc[kResPerThread][4];
 #pragma unroll
             for (int u = 0; u < kResPerThread; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
@@ -1209,15 +1201,11 @@ cudaError_t configure_kernels() {
     const int big = 200 * 1024;
     if ((e = cudaFuncSetAttribute(k_analyse, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_synthesise, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<0, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<1, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<1, QuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<2, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<2, QuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<4, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<4, QuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<8, NoQuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_ola_resample<8, QuadTab>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_ola_resample<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<8, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
@@ -1353,22 +1341,18 @@ int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out) {
 
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
                          long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
-                         long run_origin, const QuadTab *quads, cudaStream_t st) {
+                         long run_origin, cudaStream_t st) {
     const int L = p.rs_active ? (int)p.rs_filt_len : 1;
     const bool quad = p.rs_active && !p.rs_direct;
-    const bool param_tab = quad && quads != nullptr && p.rs_table_len <= kQuadParamMax;
     const int max_in = ((run * max_consumed + L + 8) + 3) & ~3;
-    const size_t sm = (quad && !param_tab ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)(max_in + (p.rs_active ? L : 0));
+    const size_t sm = (quad ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)(max_in + (p.rs_active ? L : 0));
     dim3 grid((nframes + run - 1) / run, g.rows);
-    const NoQuadTab none{};
-#define PV_OLA(OVV, TAB, ARG) k_ola_resample<OVV, TAB><<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, run_origin, ARG)
-#define PV_OLA2(OVV) do { if (param_tab) PV_OLA(OVV, QuadTab, *quads); else PV_OLA(OVV, NoQuadTab, none); } while (0)
-    if (!quad) PV_OLA(0, NoQuadTab, none);
-    else if (p.rs_oversample == 8) PV_OLA2(8);
-    else if (p.rs_oversample == 4) PV_OLA2(4);
-    else if (p.rs_oversample == 2) PV_OLA2(2);
-    else PV_OLA2(1);
-#undef PV_OLA2
+#define PV_OLA(OVV) k_ola_resample<OVV><<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, run_origin)
+    if (!quad) PV_OLA(0);
+    else if (p.rs_oversample == 8) PV_OLA(8);
+    else if (p.rs_oversample == 4) PV_OLA(4);
+    else if (p.rs_oversample == 2) PV_OLA(2);
+    else PV_OLA(1);
 #undef PV_OLA
 }
 

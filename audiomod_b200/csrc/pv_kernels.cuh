@@ -83,10 +83,6 @@ void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag,
 // sinc-table phase, output order inside a bucket, buckets padded to multiples of kResBlock.  Entry = (tap-0 position relative to
 // u_lo + kResPad) << 16 | (output position relative to out_first); 0xffffffff = padding.  rs_frac holds the cubic
 // interpolation fraction of each entry (interpolated mode) or the table phase as raw bits (direct mode).
-// The sinc "quad" table of the interpolated resampler travels as a kernel parameter when it fits (constant bank: every
-// access in the tap loop is warp-uniform, so it costs no shared-memory bandwidth); larger tables are staged in shared memory.
-constexpr int kQuadParamMax = 1040;   // filt_len * oversample + 8 <= 1032 for every ratio up to 16x at quality 4
-struct QuadTab { float4 q[kQuadParamMax]; };
 constexpr int kMaxBuckets = 8;      // resampler table phases (oversample <= 8 at quality 4)
 constexpr int kResPerThread = 4;    // outputs a thread of k_ola_resample accumulates at once
 constexpr int kResBlock = 32 * kResPerThread;   // entries a warp takes per step; buckets are padded to this
@@ -107,7 +103,7 @@ int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out);
 // be run_origin + a multiple of run), max_consumed = the largest number of normalised samples any slice contributes
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
                          long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
-                         long run_origin, const QuadTab *quads /*host copy of p.rs_quads, or null*/, cudaStream_t st);
+                         long run_origin, cudaStream_t st);
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
 
