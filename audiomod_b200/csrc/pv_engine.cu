@@ -625,7 +625,11 @@ int pvgpu_batch_create(const pvgpu_config *cfg, int n_streams, int64_t max_in_sa
     CU(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
     for (auto &c : b->ctx) {
         CU(cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&c.st_b, cudaStreamNonBlocking));
+        {   // the phase + synthesis stage holds the latency-bound serial chain: its CTAs go first when SM slots free up
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(cudaStreamCreateWithPriority(&c.st_b, cudaStreamNonBlocking, hi));
+        }
         CU(cudaStreamCreateWithFlags(&c.st_c, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
         for (int i = 0; i < 4; ++i) {
