@@ -92,7 +92,7 @@ struct Pipeline {
     Tables t;
     DevPlan p{};
     int device = 0;
-    DevBuf b_window, b_twf, b_twi, b_stwf, b_stwi, b_perm, b_omega, b_rstab, b_rsquad;
+    DevBuf b_window, b_twf, b_twi, b_stwf, b_stwi, b_perm, b_omega, b_rstab, b_rsquad, b_warp;
     // schedule on the device
     DevBuf b_recs, b_norm, b_whisper, b_carmag, b_carph;
     long recs_base = 0, recs_count = 0;
@@ -190,6 +190,28 @@ struct Pipeline {
             if ((rc = upload(b_rsquad, quads.data(), sizeof(float) * quads.size()))) return rc;
         }
         p.rs_quads = b_rsquad.as<float4>();
+        p.warp_tab = nullptr;
+        if (cartesian() && cartesian_lock() && d.freq_comp != 0.f) {
+            // freqCompSlice (phasevocoderprocess.cc:842-923) for the Cartesian pipeline: target bin i = gain * locked bin src(i)
+            // turned by delta_omega = 2*pi*hop*(i - src)/N (double expression narrowed to float like the reference's data_type)
+            const int half = d.N / 2;
+            std::vector<float> tab((size_t)4 * (half + 1));
+            for (int i = 0; i <= half; ++i) {
+                float wr = d.fixed_gain, wi = 0.f;
+                int src = i;
+                if (d.freq_comp > 1.0f || i < half) {   // the expanding direction leaves the Nyquist bin alone
+                    src = (int)std::lrint((float)i * d.freq_comp);
+                    if (src > half) { src = 0; wr = 0.f; wi = 0.f; }
+                    else {
+                        const float dw = (float)((2 * M_PI * (size_t)d.hop * (i - src)) / (double)d.N);
+                        wr = (float)(d.fixed_gain * std::cos((double)dw)); wi = (float)(d.fixed_gain * std::sin((double)dw));
+                    }
+                }
+                tab[4 * i] = wr; tab[4 * i + 1] = wi; std::memcpy(&tab[4 * i + 2], &src, sizeof src); tab[4 * i + 3] = 0.f;
+            }
+            if ((rc = upload(b_warp, tab.data(), sizeof(float) * tab.size()))) return rc;
+            p.warp_tab = b_warp.as<float4>();
+        }
         return PVGPU_OK;
     }
 
@@ -206,7 +228,7 @@ struct Pipeline {
     // The phase-locked core of the plain shift / stretch modes also runs on Cartesian spectra (k_phase_lock_c): locking a
     // region is one rotation of its bins, and the analysis phase is only ever needed at the peaks.
     bool cartesian_lock() const {
-        return d.cfg.coremode == 1 && !(d.robotic || d.whisper || d.vocoder || d.constant_mode) && p.freq_comp == 0.f;
+        return d.cfg.coremode == 1 && !(d.robotic || d.whisper || d.vocoder || d.constant_mode);
     }
     bool cartesian() const {
         const bool templated = p.N == 512 || p.N == 1024 || p.N == 2048 || p.N == 4096 || p.N == 8192;

@@ -796,7 +796,9 @@ struct SynthBinLoader {
     __device__ __forceinline__ float2 operator()(int i) const { return finish(load(i)); }
 };
 
-template <int N, bool kLock>   // kLock: Cartesian spectra of the phase-locked core only (g.synth_kind == 4), no other mode's code
+// kLock: Cartesian spectra of the phase-locked core only (g.synth_kind == 4), no other mode's code; kWarp: + the formant /
+// gender frequency warp (p.warp_tab)
+template <int N, bool kLock, bool kWarp>
 __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(const DevPlan p, const DevRows g, const float *__restrict__ car_mag,
                                                                                  const float *__restrict__ car_phase, long k0, int nf, int total) {
     constexpr int NC = N / 2;
@@ -825,27 +827,47 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
         constexpr int U = Q >= 4 ? 4 : Q;
         const int sa = fft_pad(fft_slot_of_input<NC>(t)), sb = fft_pad(fft_slot_of_input<NC>((T - t) & (T - 1)));
         const float inv_n = p.inv_n;
+        // formant / gender modes: freqCompSlice (:842-923) as a gather -- target bin i takes the locked bin src(i) turned by
+        // 2*pi*hop*(i - src)/N and scaled by the fixed gain; the host tabulates (gain cos, gain sin, src) per target bin
+        const float4 *__restrict__ wt = kWarp ? p.warp_tab : nullptr;
 #pragma unroll 1
         for (int q0 = 0; q0 < Q; q0 += U) {
             float2 lo[U], hi[U];
+            int sl[U], sh[U];
+            float2 wl[U], wh[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int kk = t + T * (q0 + u);
-                lo[u] = make_float2(gre[kk], gim[kk]);
-                hi[u] = make_float2(gre[NC - kk], gim[NC - kk]);
+                sl[u] = kk; sh[u] = NC - kk;
+                if (kWarp) {
+                    const float4 a4 = __ldg(&wt[kk]), b4 = __ldg(&wt[NC - kk]);
+                    sl[u] = __float_as_int(a4.z); sh[u] = __float_as_int(b4.z);
+                    wl[u] = make_float2(a4.x, a4.y); wh[u] = make_float2(b4.x, b4.y);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                lo[u] = make_float2(gre[sl[u]], gim[sl[u]]);
+                hi[u] = make_float2(gre[sh[u]], gim[sh[u]]);
             }
             if (locked) {
                 float2 cl[U], ch[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int kk = t + T * (q0 + u);
-                    cl[u] = lcsn[lmap[kk]];
-                    ch[u] = kk == 0 ? make_float2(1.f, 0.f) : lcsn[lmap[NC - kk]];   // bin NC (Nyquist) is not part of any region
+                    cl[u] = lcsn[lmap[sl[u]]];
+                    ch[u] = sh[u] >= NC ? make_float2(1.f, 0.f) : lcsn[lmap[sh[u]]];   // bin NC (Nyquist) is not part of any region
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     lo[u] = make_float2(lo[u].x * cl[u].x - lo[u].y * cl[u].y, lo[u].x * cl[u].y + lo[u].y * cl[u].x);
                     hi[u] = make_float2(hi[u].x * ch[u].x - hi[u].y * ch[u].y, hi[u].x * ch[u].y + hi[u].y * ch[u].x);
+                }
+            }
+            if (kWarp) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    lo[u] = make_float2(lo[u].x * wl[u].x - lo[u].y * wl[u].y, lo[u].x * wl[u].y + lo[u].y * wl[u].x);
+                    hi[u] = make_float2(hi[u].x * wh[u].x - hi[u].y * wh[u].y, hi[u].x * wh[u].y + hi[u].y * wh[u].x);
                 }
             }
 #pragma unroll
@@ -868,11 +890,15 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
             }
         }
         if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)
-            float2 fk = make_float2(gre[NC / 2], gim[NC / 2]);
-            if (locked) {
-                const float2 cs = lcsn[lmap[NC / 2]];
+            int src = NC / 2;
+            float2 w = make_float2(1.f, 0.f);
+            if (kWarp) { const float4 a4 = __ldg(&wt[NC / 2]); src = __float_as_int(a4.z); w = make_float2(a4.x, a4.y); }
+            float2 fk = make_float2(gre[src], gim[src]);
+            if (locked && src < NC) {
+                const float2 cs = lcsn[lmap[src]];
                 fk = make_float2(fk.x * cs.x - fk.y * cs.y, fk.x * cs.y + fk.y * cs.x);
             }
+            if (kWarp) fk = make_float2(fk.x * w.x - fk.y * w.y, fk.x * w.y + fk.y * w.x);
             fk = make_float2(__fmul_rn(fk.x, inv_n), __fmul_rn(fk.y, inv_n));
             const float2 fnkc = make_float2(fk.x, -fk.y);
             const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
@@ -1313,8 +1339,11 @@ static void launch_synthesise_t(const DevPlan &p, const DevRows &g, const float 
     using S = FftShape<N / 2>;
     constexpr int T = S::kThreads, G = (T >= 256) ? 1 : 256 / T;
     const int total = nframes * g.rows;
-    if (g.synth_kind == 4) k_synthesise_t<N, true><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
-    else k_synthesise_t<N, false><<<(total + G - 1) / G, T >= 256 ? T : 256, sizeof(float2) * G * S::kPadded, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
+    const int grid = (total + G - 1) / G, block = T >= 256 ? T : 256;
+    const size_t sm = sizeof(float2) * G * S::kPadded;
+    if (g.synth_kind == 4 && p.warp_tab != nullptr) k_synthesise_t<N, true, true><<<grid, block, sm, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
+    else if (g.synth_kind == 4) k_synthesise_t<N, true, false><<<grid, block, sm, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
+    else k_synthesise_t<N, false, false><<<grid, block, sm, st>>>(p, g, car_mag, car_phase, k0, nframes, total);
 }
 
 void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag, const float *car_phase, long k0, int nframes, cudaStream_t st) {

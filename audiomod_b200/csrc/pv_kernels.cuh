@@ -23,6 +23,7 @@ struct DevPlan {
     double two_pi_hop;                  // 2*M_PI*hop  (double product, phasevocoderprocess.cc:625)
     // frequency-axis warp (formant / gender), 0 = off
     float freq_comp, fixed_gain;
+    const float4 *warp_tab;             // Cartesian pipeline: per target bin (gain cos dw, gain sin dw, source bin as int bits, 0), or null
     // resampler
     int rs_active, rs_direct;
     uint32_t rs_num, rs_den, rs_filt_len, rs_oversample;
