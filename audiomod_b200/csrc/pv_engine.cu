@@ -225,8 +225,8 @@ struct Pipeline {
 
     // Modes that never use the analysis phase keep Cartesian spectra (no sqrtf / atan2f per bin in the analysis kernel); only
     // the templated FFT sizes have that variant.
-    // The phase-locked core of the plain shift / stretch modes also runs on Cartesian spectra (k_phase_lock_c): locking a
-    // region is one rotation of its bins, and the analysis phase is only ever needed at the peaks.
+    // The phase-locked core (coremode 1) of the shift / stretch / formant / gender modes also runs on Cartesian spectra
+    // (pv_lock.cuh): locking a region is one rotation of its bins, and the analysis phase is only ever needed at the peaks.
     bool cartesian_lock() const {
         return d.cfg.coremode == 1 && !(d.robotic || d.whisper || d.vocoder || d.constant_mode);
     }

@@ -64,7 +64,7 @@ struct DevRows {
     long aux_base;            // slice index of element 0 of the whisper table / carrier spectra
     int spec;                 // 0: spectra are (mag, phase); 1: Cartesian (re in mag[], im in phase[]) -- modes that never use the
                               //    analysis phase (robotic, whisper, vocoder, constant) and the phase-locked core of the plain
-                              //    shift / stretch modes (k_phase_lock_c) skip sqrtf/atan2f in the analysis kernel
+                              //    shift / stretch / formant / gender modes (k_lock_peaks + k_lock_chain) skip sqrtf/atan2f in the analysis kernel
     int synth_kind;           // 0: phases come from the spectra; 1: robotic (phase 0); 2: whisper (phase table); 3: constant;
                               // 4: Cartesian phase-locked core (rotate every bin by its region's (cos, sin))
     const float *whisper;     // [slices][channels][H] phases of the whisper mode (indexed by absolute slice - aux_base)
