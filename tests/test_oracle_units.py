@@ -53,3 +53,25 @@ def test_forward_inverse_polar_roundtrip(oracle):
         y = oracle.inverse_polar(mag, ph, n)
         w, _ = oracle.hann(n)
         assert np.allclose(y / n, x * w * w, atol=2e-5)
+
+
+def test_squared_magnitude_peak_shortcut_is_exact():
+    """k_lock_peaks decides the reference's strict `mag[b] > mag[n]` on squared magnitudes (audiomod_b200/csrc/pv_lock.cuh,
+    lock_is_peak): q_b <= q_n -> false, q_b > q_n * (1 + 2^-21) and q_b > 1e-30 -> true, otherwise the exactly rounded
+    square roots decide.  The two shortcuts must agree with comparing sqrtf values for every pair, in particular near ties."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    n = 2_000_000
+    qn = (rng.random(n).astype(np.float32) + np.float32(1e-3)) * np.float32(10.0) ** rng.integers(-28, 8, n).astype(np.float32)
+    # neighbours a few ulps to a few 2^-21 apart, on both sides, plus unrelated pairs
+    steps = rng.integers(-40, 41, n).astype(np.int32)
+    qb = qn.copy()
+    qb[: n // 2] = (qn[: n // 2].view(np.int32) + steps[: n // 2]).view(np.float32)
+    qb[n // 2:] = qn[n // 2:] * (np.float32(1.0) + rng.random(n - n // 2).astype(np.float32) * np.float32(4e-6) - np.float32(1e-6)).astype(np.float32)
+    qb = np.abs(qb).astype(np.float32)
+    truth = np.sqrt(qb, dtype=np.float32) > np.sqrt(qn, dtype=np.float32)
+    not_greater = ~(qb > qn)
+    sure = (qb > qn * np.float32(1.00000048)) & (qb > np.float32(1e-30))
+    assert not np.any(truth & not_greater), "q_b <= q_n must imply sqrtf(q_b) <= sqrtf(q_n)"
+    assert np.all(truth[sure]), "q_b > q_n (1 + 2^-21) must imply sqrtf(q_b) > sqrtf(q_n)"
+    assert np.any(~truth & ~not_greater), "the sample must contain rounded-square-root ties (the case the fallback exists for)"
