@@ -1235,6 +1235,13 @@ cudaError_t configure_kernels() {
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<4, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_phase_lock_t<8, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    // (per device: configure_kernels runs for every pipeline's device)
+#define PV_LOCK_ATTR(NN) \
+    if ((e = cudaFuncSetAttribute(k_lock_peaks<NN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e; \
+    if ((e = cudaFuncSetAttribute(k_lock_peaks<NN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e; \
+    if ((e = cudaFuncSetAttribute(k_lock_peaks<NN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    PV_LOCK_ATTR(512) PV_LOCK_ATTR(1024) PV_LOCK_ATTR(2048) PV_LOCK_ATTR(4096) PV_LOCK_ATTR(8192)
+#undef PV_LOCK_ATTR
     if ((e = cudaFuncSetAttribute(k_lock_chain<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_lock_chain<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_lock_chain<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
@@ -1298,8 +1305,6 @@ int lock_rec_stride(const DevPlan &p, int maxpk) { return maxpk > p.half / 2 ? m
 
 template <int N, int kC>
 static void launch_lock_peaks_nc(const DevPlan &p, const DevRows &g, const SliceRec *recs, long recs_base, long k0, int nframes, cudaStream_t st) {
-    static bool configured = false;   // > 48 KB of dynamic shared memory for the larger sizes
-    if (!configured) { cudaFuncSetAttribute(k_lock_peaks<N, kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); configured = true; }
     const dim3 grid((nframes + kLockRun - 1) / kLockRun, g.rows / g.channels);
     k_lock_peaks<N, kC><<<grid, LockShape<N>::kThreads, lock_peaks_smem(p.half, g.channels, g.maxpk), st>>>(p, g, recs, recs_base, k0, nframes);
 }
