@@ -92,7 +92,7 @@ struct Pipeline {
     Tables t;
     DevPlan p{};
     int device = 0;
-    DevBuf b_window, b_twf, b_twi, b_stwf, b_stwi, b_perm, b_omega, b_rstab, b_rsquad, b_warp;
+    DevBuf b_window, b_twf, b_twi, b_stwf, b_stwi, b_perm, b_omega, b_rstab, b_rsquad, b_warp, b_tw2f, b_tw2i, b_tw3f, b_tw3i;
     // schedule on the device
     DevBuf b_recs, b_norm, b_whisper, b_carmag, b_carph;
     long recs_base = 0, recs_count = 0;
@@ -173,6 +173,46 @@ struct Pipeline {
         if (p.rs_active && (rc = upload(b_rstab, d.rs.table.data(), sizeof(float) * d.rs.table.size()))) return rc;
         p.window = b_window.as<float>();
         p.tw_fwd = b_twf.as<float2>(); p.tw_inv = b_twi.as<float2>();
+        p.tw2_fwd = p.tw2_inv = p.tw3_fwd = p.tw3_inv = nullptr;
+        {   // per-pass twiddle tables of the register-tiled FFT (pv_fft.cuh): the KissFFT twiddles in [entry][k] order
+            const int nc = d.N / 2;
+            if (nc == 256 || nc == 512 || nc == 1024 || nc == 2048 || nc == 4096) {
+                const bool r2 = nc == 512 || nc == 2048;
+                const int mid = r2 ? 8 : 16, last = mid * 16, T = nc / 16;
+                auto pair_table = [&](const std::vector<float> &tw, int M) {
+                    std::vector<float> out((size_t)2 * 15 * M);
+                    const int Fa = nc / (4 * M), Fb = nc / (16 * M);
+                    for (int k = 0; k < M; ++k) {
+                        int idx[15] = {k * Fa, 2 * k * Fa, 3 * k * Fa};
+                        for (int j1 = 0; j1 < 4; ++j1) { const int kk = k + j1 * M; idx[3 + 3 * j1] = kk * Fb; idx[4 + 3 * j1] = 2 * kk * Fb; idx[5 + 3 * j1] = 3 * kk * Fb; }
+                        for (int e = 0; e < 15; ++e) { out[2 * ((size_t)e * M + k)] = tw[2 * idx[e]]; out[2 * ((size_t)e * M + k) + 1] = tw[2 * idx[e] + 1]; }
+                    }
+                    return out;
+                };
+                auto single_table = [&](const std::vector<float> &tw) {
+                    std::vector<float> out((size_t)2 * 12 * T);
+                    for (int t = 0; t < T; ++t)
+                        for (int q = 0; q < 4; ++q)
+                            for (int m = 1; m <= 3; ++m) {
+                                const int idx = m * (t + T * q);
+                                const size_t o = (size_t)(3 * q + m - 1) * T + t;
+                                out[2 * o] = tw[2 * idx]; out[2 * o + 1] = tw[2 * idx + 1];
+                            }
+                    return out;
+                };
+                const std::vector<float> f2 = pair_table(t.tw_fwd, mid), i2 = pair_table(t.tw_inv, mid);
+                if ((rc = upload(b_tw2f, f2.data(), sizeof(float) * f2.size()))) return rc;
+                if ((rc = upload(b_tw2i, i2.data(), sizeof(float) * i2.size()))) return rc;
+                p.tw2_fwd = b_tw2f.as<float2>(); p.tw2_inv = b_tw2i.as<float2>();
+                if (nc / last == 16 || nc / last == 4) {
+                    const std::vector<float> f3 = nc / last == 16 ? pair_table(t.tw_fwd, last) : single_table(t.tw_fwd);
+                    const std::vector<float> i3 = nc / last == 16 ? pair_table(t.tw_inv, last) : single_table(t.tw_inv);
+                    if ((rc = upload(b_tw3f, f3.data(), sizeof(float) * f3.size()))) return rc;
+                    if ((rc = upload(b_tw3i, i3.data(), sizeof(float) * i3.size()))) return rc;
+                    p.tw3_fwd = b_tw3f.as<float2>(); p.tw3_inv = b_tw3i.as<float2>();
+                }
+            }
+        }
         p.stw_fwd = b_stwf.as<float2>(); p.stw_inv = b_stwi.as<float2>();
         p.perm = b_perm.as<uint16_t>();
         p.omega = b_omega.as<float>();

@@ -101,30 +101,32 @@ __device__ __forceinline__ void fft_first_pass(float2 (&v)[16], const float2 *__
 }
 
 // Pair pass: stages (radix 4, span M) + (radix 4, span 4M) on the set {base + k + j*M, j < 16}; v[j] holds element j.
+// The twiddles of the later passes are read from per-pass tables laid out [entry][k] (fft_pass_table on the host builds them
+// from the KissFFT table, same values): the lanes of a warp have consecutive k, so every load is one contiguous line instead
+// of a gather with a 128-byte stride through the original table (which made the L1 data pipe the limiter of both FFT kernels).
+//   pair pass, span M:  entries 0..2 = tw[{1,2,3} * k * Fa], entries 3 + 3*j1 + {0,1,2} = tw[{1,2,3} * (k + j1*M) * Fb]
 template <int NC, int M, bool kInverse>
-__device__ __forceinline__ void fft_pair_pass(float2 (&v)[16], int k, const float2 *__restrict__ tw) {
-    constexpr int Fa = NC / (4 * M), Fb = NC / (16 * M);
+__device__ __forceinline__ void fft_pair_pass(float2 (&v)[16], int k, const float2 *__restrict__ twp) {
     {
-        const float2 t1 = __ldg(&tw[k * Fa]), t2 = __ldg(&tw[2 * k * Fa]), t3 = __ldg(&tw[3 * k * Fa]);
+        const float2 t1 = __ldg(&twp[k]), t2 = __ldg(&twp[M + k]), t3 = __ldg(&twp[2 * M + k]);
 #pragma unroll
         for (int g = 0; g < 4; ++g) bfly4<kInverse>(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], t1, t2, t3);
     }
 #pragma unroll
-    for (int j1 = 0; j1 < 4; ++j1) {
-        const int kk = k + j1 * M;
-        bfly4<kInverse>(v[j1], v[4 + j1], v[8 + j1], v[12 + j1], __ldg(&tw[kk * Fb]), __ldg(&tw[2 * kk * Fb]), __ldg(&tw[3 * kk * Fb]));
-    }
+    for (int j1 = 0; j1 < 4; ++j1)
+        bfly4<kInverse>(v[j1], v[4 + j1], v[8 + j1], v[12 + j1], __ldg(&twp[(3 + 3 * j1) * M + k]), __ldg(&twp[(4 + 3 * j1) * M + k]),
+                        __ldg(&twp[(5 + 3 * j1) * M + k]));
 }
 
 // Single last stage (radix 4, span M = NC/4): four butterflies per thread, v[4q + j] = element (t + T*q) + j*M.
+//   single pass: entries 3*q + {0,1,2} = tw[{1,2,3} * (t + T*q)], table laid out [entry][t]
 template <int NC, bool kInverse>
-__device__ __forceinline__ void fft_single_pass(float2 (&v)[16], int t, const float2 *__restrict__ tw) {
+__device__ __forceinline__ void fft_single_pass(float2 (&v)[16], int t, const float2 *__restrict__ twp) {
     constexpr int T = FftShape<NC>::kThreads;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k = t + T * q;
-        bfly4<kInverse>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], __ldg(&tw[k]), __ldg(&tw[2 * k]), __ldg(&tw[3 * k]));
-    }
+    for (int q = 0; q < 4; ++q)
+        bfly4<kInverse>(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3], __ldg(&twp[(3 * q) * T + t]), __ldg(&twp[(3 * q + 1) * T + t]),
+                        __ldg(&twp[(3 * q + 2) * T + t]));
 }
 
 // Barrier over the threads of one frame.  Frames owned by less than / exactly one warp use __syncwarp; larger groups a
@@ -160,7 +162,8 @@ template <int NC> __device__ __forceinline__ int fft_out_index(int t, int i) { r
 // padded positions and the frame's threads have synchronised; on exit v[] holds this thread's outputs and
 // fft_out_index() tells which.  The caller decides whether the outputs go back to buf (analysis) or out to memory.
 template <int NC, bool kInverse>
-__device__ __forceinline__ void fft_frame(float2 (&v)[16], float2 *buf, int t, int group, const float2 *__restrict__ tw) {
+__device__ __forceinline__ void fft_frame(float2 (&v)[16], float2 *buf, int t, int group, const float2 *__restrict__ tw,
+                                          const float2 *__restrict__ tw2 /*second pass*/, const float2 *__restrict__ tw3 /*third pass*/) {
     using S = FftShape<NC>;
     constexpr int T = S::kThreads;
     {
@@ -178,7 +181,7 @@ __device__ __forceinline__ void fft_frame(float2 (&v)[16], float2 *buf, int t, i
         float2 *b2 = buf + fft_pad((t / M) * (16 * M) + k);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = b2[fft_pad(j * M)];
-        fft_pair_pass<NC, M, kInverse>(v, k, tw);
+        fft_pair_pass<NC, M, kInverse>(v, k, tw2);
         if (NC > 256) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) b2[fft_pad(j * M)] = v[j];
@@ -192,14 +195,14 @@ __device__ __forceinline__ void fft_frame(float2 (&v)[16], float2 *buf, int t, i
             const float2 *b3 = buf + fft_pad((t / M) * (16 * M) + k);
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = b3[fft_pad(j * M)];
-            fft_pair_pass<NC, M, kInverse>(v, k, tw);
+            fft_pair_pass<NC, M, kInverse>(v, k, tw3);
         } else {
             const float2 *b3 = buf + fft_pad(t);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[4 * q + j] = b3[fft_pad(T * q + j * M)];
-            fft_single_pass<NC, kInverse>(v, t, tw);
+            fft_single_pass<NC, kInverse>(v, t, tw3);
         }
     }
 }

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
     }
     frame_sync<T>(group);
     float2 v[16];
-    if (active) fft_frame<NC, false>(v, buf, t, group, p.tw_fwd);
+    if (active) fft_frame<NC, false>(v, buf, t, group, p.tw_fwd, p.tw2_fwd, p.tw3_fwd);
     else { if (NC > 256) { frame_sync<T>(group); } frame_sync<T>(group); }
     frame_sync<T>(group);   // all reads of the last pass are done before the natural-order write-back
     if (active) {
@@ -958,7 +958,7 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
     }
     frame_sync<T>(group);
     float2 v[16];
-    if (active) fft_frame<NC, true>(v, buf, t, group, p.tw_inv);
+    if (active) fft_frame<NC, true>(v, buf, t, group, p.tw_inv, p.tw2_inv, p.tw3_inv);
     else { if (NC > 256) { frame_sync<T>(group); } frame_sync<T>(group); }
     if (!active) return;
     // ifftshift + synthesis window (impl.h:183-198, :1052-1056): complex output o holds samples 2o, 2o+1 of the

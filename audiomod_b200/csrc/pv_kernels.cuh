@@ -16,6 +16,7 @@ struct DevPlan {
     int radix[kMaxStages], span[kMaxStages];
     const float *window;                // N
     const float2 *tw_fwd, *tw_inv;      // nc
+    const float2 *tw2_fwd, *tw2_inv, *tw3_fwd, *tw3_inv;   // the same twiddles in the second / third pass's access order (pv_fft.cuh)
     const float2 *stw_fwd, *stw_inv;    // nc
     const uint16_t *perm;               // nc
     const float *omega;                 // half
