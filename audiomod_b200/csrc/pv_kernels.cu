@@ -155,7 +155,13 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
         float x0[16], x1[16];
         if (kS16) {
             const short *__restrict__ xp = (const short *)g.in + xoff + 2 * t;
-            if (valid == N) {   // whole frame inside the stream: no per-sample bounds
+            if (valid == N && ((reinterpret_cast<uintptr_t>(xp) & 3) == 0)) {   // even frame start: one 32-bit load per sample pair
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const short2 xx = *(const short2 *)(xp + 2 * T * i);
+                    x0[i] = (float)xx.x * (1.0f / 32768.0f); x1[i] = (float)xx.y * (1.0f / 32768.0f);
+                }
+            } else if (valid == N) {   // whole frame inside the stream: no per-sample bounds
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { x0[i] = (float)xp[2 * T * i] * (1.0f / 32768.0f); x1[i] = (float)xp[2 * T * i + 1] * (1.0f / 32768.0f); }
             } else {
@@ -168,7 +174,10 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_analyse_t(con
             }
         } else {
             const float *__restrict__ xp = (const float *)g.in + xoff + 2 * t;
-            if (valid == N) {
+            if (valid == N && ((reinterpret_cast<uintptr_t>(xp) & 7) == 0)) {   // even frame start: one 64-bit load per sample pair
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { const float2 xx = *(const float2 *)(xp + 2 * T * i); x0[i] = xx.x; x1[i] = xx.y; }
+            } else if (valid == N) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) { x0[i] = xp[2 * T * i]; x1[i] = xp[2 * T * i + 1]; }
             } else {
