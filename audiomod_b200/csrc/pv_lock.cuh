@@ -45,7 +45,7 @@ __device__ __forceinline__ bool lock_is_peak(float qb, float qmax) {
 // shared-memory layout of k_lock_peaks, in floats: where the bin->region maps start (16-byte aligned) and the total
 __host__ __device__ inline int lock_peaks_map_offset(int half, int C, int maxpk) { return (3 * half + 8 + 2 * C * half + 3 * maxpk + 1 + 32 + 3) & ~3; }
 inline size_t lock_peaks_smem(int half, int C, int maxpk) {
-    return sizeof(float) * (size_t)lock_peaks_map_offset(half, C, maxpk) + sizeof(unsigned short) * (size_t)C * half + 2 * sizeof(float) * (size_t)C * maxpk;
+    return sizeof(float) * (size_t)lock_peaks_map_offset(half, C, maxpk) + sizeof(unsigned short) * (size_t)C * half + 4 * sizeof(float) * (size_t)C * maxpk;
 }
 inline size_t lock_chain_smem(int half, int C, int maxpk) { return sizeof(float) * ((size_t)C * 2 * maxpk + (size_t)C * half) + sizeof(int) * 2 * (size_t)C; }
 
@@ -80,9 +80,9 @@ __global__ void __launch_bounds__(LockShape<N>::kThreads, LockShape<N>::kMinBloc
     const int b0 = tid * E;
     const int fa = blockIdx.x * kLockRun, fb = min(fa + kLockRun, nframes);
     const int f_first = (k0 + fa > 0) ? fa - 1 : fa;   // a frame before the run exists: warm up on it (peaks, regions, spectrum)
-    float *s_cph = (float *)(s_map + C * half);       // C * maxpk  phi at the peaks of the channel's latest frame ...
-    int *s_cpk = (int *)(s_cph + C * maxpk);          // C * maxpk  ... and their bins (valid while bit c of cache_ok is set)
-    unsigned cache_ok = 0;
+    float *s_cph = (float *)(s_map + C * half);       // C * 2 * maxpk  phi at the peaks of the channel's latest frame (ping-pong) ...
+    int *s_cpk = (int *)(s_cph + C * 2 * maxpk);      // C * 2 * maxpk  ... and their bins (valid while bit c of cache_ok is set)
+    unsigned cache_ok = 0, cache_side = 0;            // bit c of cache_side: which half holds the channel's latest frame
 
     // (frame slot, channel) of the next fetch; slot -1 is the last frame of the previous launch (lock_tail)
     float pre[E], pim[E];
@@ -149,10 +149,13 @@ __global__ void __launch_bounds__(LockShape<N>::kThreads, LockShape<N>::kMinBloc
             for (int e = 0; e < E; ++e) {
                 const int b = b0 + e;
                 const float qmax = fmaxf(fmaxf(w[e], w[e + 1]), fmaxf(w[e + 3], w[e + 4]));
-                const bool pk = b >= 2 && b + 2 < half && lock_is_peak(w[e + 2], qmax);
-                flags |= (unsigned)pk << e;
-                cnt += pk;
+                (void)b;
+                flags |= (unsigned)lock_is_peak(w[e + 2], qmax) << e;
             }
+            // 2 <= b <= half - 3 (:587): only the first and the last thread own excluded bins
+            if (tid == 0) flags &= ~3u;
+            if (tid == nthr - 1) flags &= ~(3u << (E - 2));
+            cnt = __popc(flags);
             int incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -172,10 +175,10 @@ __global__ void __launch_bounds__(LockShape<N>::kThreads, LockShape<N>::kMinBloc
             const int npk = __shfl_sync(0xffffffffu, ws, nwarp - 1);
             int base = __shfl_sync(0xffffffffu, ws, (warp + 31) & 31);   // inclusive total of warp - 1; warp 0 reads lane 31 (discarded)
             base = (warp == 0 ? 0 : base) + incl - cnt;   // peaks before this thread's first bin
-            {
-                int r = base;
-#pragma unroll
-                for (int e = 0; e < E; ++e) if (flags & (1u << e)) s_cur[r++] = b0 + e;
+            if (flags) {   // peaks are at least 3 bins apart: at most two in 4 bins, three in 8
+                s_cur[base] = b0 + __ffs(flags) - 1;
+                if (cnt > 1) s_cur[base + cnt - 1] = b0 + 31 - __clz(flags);
+                if (E == 8 && cnt > 2) s_cur[base + 1] = b0 + __ffs(flags & (flags - 1)) - 1;
             }
             const int64_t slot = (row0 + c) * g.F + f;    // (row, frame slot); not used while warming up
             const bool first = k_is_0 && c == 0;          // first call of the process (:602-616)
@@ -184,15 +187,16 @@ __global__ void __launch_bounds__(LockShape<N>::kThreads, LockShape<N>::kMinBloc
             __syncthreads();   // (C) peak list complete
             for (int r = tid; r <= npk; r += nthr)   // region starts (:668-683): round((a + b) * 0.5), half away from zero
                 s_start[r] = r == 0 ? 0 : r == npk ? half : (s_cur[r - 1] + s_cur[r] + 1) >> 1;
-            float php_r[2];   // phi at this thread's peaks (r = tid, tid + nthr), kept for the cache
             if (lock_now) {
                 const float phase_inc = (float)rec_f[f].phase_inc;
                 float4 *__restrict__ out = g.lock_rec + slot * g.rec_stride;
                 const bool cached = (cache_ok >> c) & 1;
-                const float *cph = s_cph + c * maxpk;
-                const int *cpk = s_cpk + c * maxpk;
-                int u = 0;
-                for (int r = tid; r < npk; r += nthr, ++u) {
+                const int cs = (cache_side >> c) & 1;
+                const float *cph = s_cph + (c * 2 + cs) * maxpk;
+                const int *cpk = s_cpk + (c * 2 + cs) * maxpk;
+                float *nph = s_cph + (c * 2 + (cs ^ 1)) * maxpk;   // this frame's peak phases: the next frame's cache
+                int *npb = s_cpk + (c * 2 + (cs ^ 1)) * maxpk;
+                for (int r = tid; r < npk; r += nthr) {
                     const int p2 = s_cur[r];
                     // nearest previous peak, ties keep the lower index (:641-652): the region of the previous iteration's
                     // frame that contains p2 belongs to the nearest peak; exactly half way the reference stays on the lower one
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(LockShape<N>::kThreads, LockShape<N>::kMinBloc
                     const float dphi = (float)__dadd_rn((double)pomega, princarg_fast((double)sub3_rn(php, a, pomega)));
                     const float adv = __fdiv_rn(__fmul_rn(dphi, phase_inc), hopf);
                     out[r] = make_float4(php, a, adv, __int_as_float(p1 | (ridx << 16)));
-                    if (u < 2) php_r[u] = php;
+                    nph[r] = php; npb[r] = p2;
                 }
             } else if (!warm && kind == 1) {
                 // classic propagation (:617-636): per bin phi, prev_phase and the advance; prev_outphase is the chain's business
@@ -254,15 +258,9 @@ __global__ void __launch_bounds__(LockShape<N>::kThreads, LockShape<N>::kMinBloc
                 *(float4 *)(A + b0 + e) = make_float4(re[e], re[e + 1], re[e + 2], re[e + 3]);
                 *(float4 *)(B + b0 + e) = make_float4(im[e], im[e + 1], im[e + 2], im[e + 3]);
             }
-            // the peak phases of a locked frame are the prev_phase of most of the next frame's links; at most two peaks per
-            // thread are cached (more only when there are more peaks than 2 * threads: then nothing is)
-            if (lock_now && npk <= 2 * nthr) {
-                int u = 0;
-                for (int r = tid; r < npk; r += nthr, ++u) { s_cph[c * maxpk + r] = php_r[u]; s_cpk[c * maxpk + r] = s_cur[r]; }
-                cache_ok |= 1u << c;
-            } else {
-                cache_ok &= ~(1u << c);
-            }
+            // the peak phases of a locked frame are the prev_phase of most of the next frame's links
+            if (lock_now) { cache_ok |= 1u << c; cache_side ^= 1u << c; }
+            else cache_ok &= ~(1u << c);
             if (!warm && tid == 0) g.lock_hdr[slot] = make_int2(npk, kind);
             { int *tsw = s_prev; s_prev = s_cur; s_cur = tsw; }
             nprev = npk;
