@@ -143,26 +143,34 @@ __global__ void __launch_bounds__(LockShape<N>::kThreads, LockShape<N>::kMinBloc
 #pragma unroll
             for (int e = 0; e < E; ++e) w[2 + e] = q[e];
             w[E + 2] = s_q[4 + b0 + E]; w[E + 3] = s_q[4 + b0 + E + 1];
-            unsigned flags = 0;
-            int cnt = 0;
+            // branch-free first: candidates (q_b above all four neighbours) and sure peaks (above them by the margin that
+            // separates the rounded square roots, lock_is_peak); the rare candidates in between take the exact-sqrt test
+            unsigned flags = 0, unsure = 0;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int b = b0 + e;
                 const float qmax = fmaxf(fmaxf(w[e], w[e + 1]), fmaxf(w[e + 3], w[e + 4]));
-                (void)b;
-                flags |= (unsigned)lock_is_peak(w[e + 2], qmax) << e;
+                const bool cand = w[e + 2] > qmax;
+                const bool sure = w[e + 2] > fmaxf(__fmul_rn(qmax, 1.00000048f), 1e-30f);
+                flags |= (unsigned)sure << e;
+                unsure |= (unsigned)(cand && !sure) << e;
+            }
+            while (unsure) {
+                const int e = __ffs(unsure) - 1;
+                unsure &= unsure - 1;
+                const float qmax = fmaxf(fmaxf(s_q[4 + b0 + e - 2], s_q[4 + b0 + e - 1]), fmaxf(s_q[4 + b0 + e + 1], s_q[4 + b0 + e + 2]));
+                flags |= (unsigned)lock_is_peak(s_q[4 + b0 + e], qmax) << e;
             }
             // 2 <= b <= half - 3 (:587): only the first and the last thread own excluded bins
             if (tid == 0) flags &= ~3u;
             if (tid == nthr - 1) flags &= ~(3u << (E - 2));
-            cnt = __popc(flags);
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            if (lane == 31) s_wsum[warp] = incl;
+            const int cnt = __popc(flags);
+            // peaks in the lanes before this one: a thread has 0..3 peaks, so three ballots count them
+            const unsigned lt = (1u << lane) - 1;
+            const unsigned b1 = __ballot_sync(0xffffffffu, cnt >= 1), b2 = __ballot_sync(0xffffffffu, cnt >= 2);
+            int excl = __popc(b1 & lt) + __popc(b2 & lt), wtot = __popc(b1) + __popc(b2);
+            if (E == 8) { const unsigned b3 = __ballot_sync(0xffffffffu, cnt >= 3); excl += __popc(b3 & lt); wtot += __popc(b3); }
+            const int incl = excl + cnt;
+            if (lane == 31) s_wsum[warp] = wtot;
             if (ff < fb) fetch();   // prefetch the next (frame, channel)
             __syncthreads();   // (B)
             // peaks in the warps before this one, and in the whole frame: a second scan over the (at most 16) warp totals
