@@ -152,6 +152,10 @@ def test_batch_ragged_matches_oracle(A, oracle, case):
     (dict(timeratio=0.5, mode=5, coremode=0, fftsize=1024, hopsize=128), 44100, 1),
     (dict(semitones=24.0, mode=0, coremode=1, fftsize=1024), 44100, 1),     # two octaves up: oversample 4 table
     (dict(semitones=-12.0, mode=0, coremode=1, fftsize=2048), 44100, 1),    # octave down: up-sampling resampler
+    (dict(semitones=3.0, mode=0, coremode=1, fftsize=8192), 44100, 2),      # phase-locked core at 8 bins per thread (up to 3 peaks each)
+    (dict(semitones=-2.0, mode=0, coremode=1, fftsize=512), 22050, 1),      # smallest templated size: two warps per stream
+    (dict(semitones=5.0, mode=2, coremode=1, fftsize=4096), 48000, 2),      # formant warp on the Cartesian pipeline, 512 threads
+    (dict(semitones=-5.0, mode=1, coremode=1, fftsize=1024), 44100, 2),     # gender change, expanding direction
 ])
 def test_unusual_sizes_and_hops(A, oracle, kw, sr, ch):
     xs = [make_input("x", sr, ch, 0.7 - 0.2 * i, 800 + i) for i in range(2)]
