@@ -341,6 +341,40 @@ struct Pipeline {
             int pos = 0;
             for (int q = 0; q < nb; ++q) {
                 hdr.start[q] = pos;
+                // A warp step takes kResBlock consecutive entries as kResPerThread rows of 32 lanes, and a row's 32 input windows are
+                // read with one shared-memory load per tap: permute every block so that the windows of a row start on different
+                // banks (start mod 32) as far as the block allows.  The order of the entries is otherwise free (each carries its
+                // output position).  Measured before: 1.9 wavefronts per load instead of 1 (the starts advance by 3, 3, 2, ...).
+                if (!p.rs_direct) {
+                    std::vector<unsigned> &e = be[q];
+                    std::vector<float> &f = bf[q];
+                    for (size_t b0 = 0; b0 < e.size(); b0 += kResBlock) {
+                        const int n = (int)std::min<size_t>(kResBlock, e.size() - b0), nrow = (n + 31) / 32;
+                        std::vector<int> rows[kResPerThread];
+                        unsigned used[kResPerThread] = {};
+                        std::vector<int> spill;
+                        for (int i = 0; i < n; ++i) {
+                            const unsigned bank = (e[b0 + i] >> 16) & 31u;
+                            int r = 0;
+                            while (r < nrow && (rows[r].size() >= 32 || (used[r] >> bank & 1u))) ++r;
+                            if (r < nrow) { rows[r].push_back(i); used[r] |= 1u << bank; }
+                            else spill.push_back(i);
+                        }
+                        size_t sp = 0;   // entries that found no conflict-free row fill the rows that are not full, last row last
+                        for (int r = 0; r < nrow; ++r) {
+                            const size_t want = r + 1 < nrow ? 32 : (size_t)(n - 32 * (nrow - 1));
+                            while (rows[r].size() < want && sp < spill.size()) rows[r].push_back(spill[sp++]);
+                            for (int r2 = nrow - 1; r2 > r && rows[r].size() < want; --r2)
+                                while (rows[r].size() < want && !rows[r2].empty()) { rows[r].push_back(rows[r2].back()); rows[r2].pop_back(); }
+                        }
+                        std::vector<unsigned> e2;
+                        std::vector<float> f2;
+                        for (int r = 0; r < nrow; ++r) for (int i : rows[r]) { e2.push_back(e[b0 + i]); f2.push_back(f[b0 + i]); }
+                        for (size_t i = sp; i < spill.size(); ++i) { e2.push_back(e[b0 + spill[i]]); f2.push_back(f[b0 + spill[i]]); }
+                        std::copy(e2.begin(), e2.end(), e.begin() + b0);
+                        std::copy(f2.begin(), f2.end(), f.begin() + b0);
+                    }
+                }
                 ent.insert(ent.end(), be[q].begin(), be[q].end());
                 frac.insert(frac.end(), bf[q].begin(), bf[q].end());
                 pos += (int)be[q].size();
