@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libpvgpu.so")
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, 1, 2, 3, 4
 F32, S16 = 0, 1
+HOST_NUMA_LOCAL, HOST_HUGEPAGES = 1, 2
 
 
 class PvgpuError(RuntimeError):
@@ -52,12 +53,25 @@ SYMBOLS = {
     "pvgpu_batch_destroy": (None, [C.c_void_p]),
     "pvgpu_batch_plan": (C.c_int, [C.c_void_p, _i64p, C.c_int, _i64p]),
     "pvgpu_batch_run_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "pvgpu_batch_synchronize": (C.c_int, [C.c_void_p]),
     "pvgpu_batch_run_host": (C.c_int, [C.c_void_p, _vpp, _vpp, C.c_int]),
     "pvgpu_batch_stats": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p, _i64p]),
     "pvgpu_batch_info": (C.c_int, [C.c_void_p, C.POINTER(Info)]),
     "pvgpu_batch_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "pvgpu_batch_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i64p]),
     "pvgpu_batch_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "pvgpu_mbatch_create": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int64, C.POINTER(C.c_int), C.c_int, _vpp]),
+    "pvgpu_mbatch_destroy": (None, [C.c_void_p]),
+    "pvgpu_mbatch_plan": (C.c_int, [C.c_void_p, _i64p, C.c_int, _i64p]),
+    "pvgpu_mbatch_run_host": (C.c_int, [C.c_void_p, _vpp, _vpp, C.c_int]),
+    "pvgpu_mbatch_stats": (C.c_int, [C.c_void_p, _i64p, _i64p, _i64p, C.POINTER(C.c_int)]),
+    "pvgpu_mbatch_owner": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "pvgpu_shard_streams": (C.c_int, [_i64p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "pvgpu_host_alloc": (C.c_int, [_vpp, C.c_size_t, C.c_int, C.c_int]),
+    "pvgpu_host_free": (C.c_int, [C.c_void_p]),
+    "pvgpu_host_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "pvgpu_device_numa_node": (C.c_int, [C.c_int]),
+    "pvgpu_bind_thread_to_device": (C.c_int, [C.c_int]),
     "pvgpu_test_forward_polar": (C.c_int, [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "pvgpu_test_inverse_polar": (C.c_int, [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "pvgpu_test_atan2f": (C.c_int, [C.c_int, C.c_int64, _fp, _fp, _fp]),

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/pvgpu.h"
+#include "pv_internal.h"
 #include "pv_kernels.cuh"
 #include "pv_plan.h"
 
@@ -28,7 +29,8 @@
 namespace pvgpu {
 
 static thread_local std::string g_err;
-static int fail(int code, const char *fmt, ...) {
+const std::string &last_error_string() { return g_err; }
+int fail(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -410,7 +412,7 @@ struct Pipeline {
         launch_analyse(p, g, k0, nf, st);
         span_end(sp, st); ++launches;
     }
-    void run_modify_synth(const DevRows &g, long k0, int nf, cudaStream_t st) {
+    int run_modify_synth(const DevRows &g, long k0, int nf, cudaStream_t st) {
         const SliceRec *recs = b_recs.as<SliceRec>();
         Span *sp;
         if (d.robotic || d.whisper) {
@@ -424,8 +426,8 @@ struct Pipeline {
             sp = span_begin(6, st); launch_lock_peaks(p, g, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches;
             // the chunk's last frame is what the next launch links to (before the chain touches classic frames in place)
             const size_t pitch = sizeof(float) * (size_t)g.F * p.Hp, w = sizeof(float) * (size_t)p.Hp;
-            cudaMemcpy2DAsync(g.lock_tail, 2 * w, g.mag + (size_t)(nf - 1) * p.Hp, pitch, w, g.rows, cudaMemcpyDeviceToDevice, st);
-            cudaMemcpy2DAsync(g.lock_tail + p.Hp, 2 * w, g.phase + (size_t)(nf - 1) * p.Hp, pitch, w, g.rows, cudaMemcpyDeviceToDevice, st);
+            CU(cudaMemcpy2DAsync(g.lock_tail, 2 * w, g.mag + (size_t)(nf - 1) * p.Hp, pitch, w, g.rows, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemcpy2DAsync(g.lock_tail + p.Hp, 2 * w, g.phase + (size_t)(nf - 1) * p.Hp, pitch, w, g.rows, cudaMemcpyDeviceToDevice, st));
             sp = span_begin(7, st); launch_lock_chain(p, g, nf, st); span_end(sp, st); ++launches;
         } else if (!d.vocoder && !d.constant_mode) {
             sp = span_begin(1, st); launch_phase_core(p, g, d.cfg.coremode, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches;
@@ -433,6 +435,7 @@ struct Pipeline {
         sp = span_begin(2, st);
         launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st);
         span_end(sp, st); ++launches;
+        return PVGPU_OK;
     }
     void run_ola(const DevRows &g, long k0, int nf, cudaStream_t st) {
         const SliceRec *recs = b_recs.as<SliceRec>();
@@ -441,10 +444,12 @@ struct Pipeline {
                             b_rsent.as<unsigned>(), b_rsfrac.as<float>(), run_origin, st);
         span_end(sp, st); ++launches;
     }
-    void run_frames(const DevRows &g, long k0, int nf, cudaStream_t st) {
+    int run_frames(const DevRows &g, long k0, int nf, cudaStream_t st) {
         run_analyse(g, k0, nf, st);
-        run_modify_synth(g, k0, nf, st);
+        int rc = run_modify_synth(g, k0, nf, st);
+        if (rc) return rc;
         run_ola(g, k0, nf, st);
+        return PVGPU_OK;
     }
 };
 
@@ -559,6 +564,7 @@ struct pvgpu_batch {
     cudaEvent_t ev_fork = nullptr;
     DevBuf d_nin, d_nout;
     cudaStream_t stream = nullptr;
+    cudaStream_t last_stream = cudaStreamLegacy;   // the caller's stream of the last pvgpu_batch_run_device
     int64_t h2d = 0, d2h = 0;
     ~pvgpu_batch() {
         for (auto &c : ctx) {
@@ -634,7 +640,7 @@ static int run_chunks(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, DevRows g, bool ove
             CU(cudaStreamWaitEvent(sb, ctx.ev_an[e], 0));
             if (ci >= 2) CU(cudaStreamWaitEvent(sb, ctx.ev_ola[e2], 0));
         }
-        pl.run_modify_synth(g, k0, nf, sb);
+        if ((rc = pl.run_modify_synth(g, k0, nf, sb))) return rc;
         if (overlap) {
             CU(cudaEventRecord(ctx.ev_syn[e], sb));
             CU(cudaStreamWaitEvent(sc, ctx.ev_syn[e], 0));
@@ -824,13 +830,20 @@ int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_
     return PVGPU_OK;
 }
 
-int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt, void *cuda_stream) {
-    if (!b || !d_in || !d_out) return fail(PVGPU_EINVAL, "null argument");
-    if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
-    if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
+// After a failed run: nothing of this batch may still be reading or writing the caller's buffers when the error is returned.
+static int drain_after_error(pvgpu_batch *b, int rc) {
+    if (rc != PVGPU_OK) {
+        const std::string keep = g_err;
+        cudaSetDevice(b->pl.device);
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
+}
+
+static int batch_run_device_impl(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt, cudaStream_t st) {
     const size_t esz = fmt == PVGPU_S16 ? sizeof(short) : sizeof(float);
-    CU(cudaSetDevice(b->pl.device));
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : b->stream;
     const int total_rows = b->n_streams * b->cfg.channels;
     const int group = b->group_rows();
     const int n_groups = (total_rows + group - 1) / group;
@@ -853,7 +866,27 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
         CU(cudaEventRecord(b->ctx[i].done, b->ctx[i].st));
         CU(cudaStreamWaitEvent(st, b->ctx[i].done, 0));
     }
-    if (!cuda_stream) CU(cudaStreamSynchronize(st));
+    return PVGPU_OK;
+}
+
+// cuda_stream is the CALLER's stream, with CUDA's own convention that a null handle is the legacy default stream: the
+// batch's internal (non-blocking) streams are forked from it and joined back into it with events, so the run is ordered
+// after everything the caller queued on that stream before the call and before everything queued after it.  The call
+// never blocks the host; pvgpu_batch_synchronize() does.
+int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt, void *cuda_stream) {
+    if (!b || !d_in || !d_out) return fail(PVGPU_EINVAL, "null argument");
+    if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
+    if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
+    CU(cudaSetDevice(b->pl.device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy;
+    b->last_stream = st;
+    return drain_after_error(b, batch_run_device_impl(b, d_in, in_stride, d_out, out_stride, fmt, st));
+}
+
+int pvgpu_batch_synchronize(pvgpu_batch *b) {
+    if (!b) return fail(PVGPU_EINVAL, "null batch");
+    CU(cudaSetDevice(b->pl.device));
+    CU(cudaStreamSynchronize(b->last_stream));
     return PVGPU_OK;
 }
 
@@ -956,12 +989,8 @@ static int run_host_timesliced(pvgpu_batch *b, const void *const *in_rows, void 
     return PVGPU_OK;
 }
 
-int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt) {
-    if (!b || !in_rows || !out_rows) return fail(PVGPU_EINVAL, "null argument");
-    if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
-    if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
+static int batch_run_host_impl(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt) {
     const size_t esz = fmt == PVGPU_S16 ? sizeof(short) : sizeof(float);
-    CU(cudaSetDevice(b->pl.device));
     const int C = b->cfg.channels;
     const int total_rows = b->n_streams * C;
     int64_t in_stride = 0, out_stride = 0;
@@ -1000,6 +1029,14 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
     }
     for (int i = 0; i < n_ctx; ++i) CU(cudaStreamSynchronize(b->ctx[i].st));
     return PVGPU_OK;
+}
+
+int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt) {
+    if (!b || !in_rows || !out_rows) return fail(PVGPU_EINVAL, "null argument");
+    if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
+    if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
+    CU(cudaSetDevice(b->pl.device));
+    return drain_after_error(b, batch_run_host_impl(b, in_rows, out_rows, fmt));
 }
 
 int pvgpu_batch_profile(pvgpu_batch *b, int enable) {
@@ -1202,7 +1239,8 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
         gc.mag = pl.b_carmag.as<float>(); gc.phase = pl.b_carph.as<float>(); gc.F = added;
         launch_analyse(p, gc, k0, added, s->st);
     }
-    for (long k = k0; k < k0 + added; k += s->ws.F) pl.run_frames(g, k, (int)std::min<long>(s->ws.F, k0 + added - k), s->st);
+    for (long k = k0; k < k0 + added; k += s->ws.F)
+        if ((rc = pl.run_frames(g, k, (int)std::min<long>(s->ws.F, k0 + added - k), s->st))) return rc;
     CU(cudaGetLastError());
     if (new_out > 0) {
         s->h_stage.resize((size_t)C * new_out);

@@ -2,6 +2,7 @@
 // expressions round exactly like the reference's default (SSE2, no FMA) build.
 #include "pv_plan.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -465,6 +466,26 @@ StreamPlan plan_stream(Scheduler &s, long n_in, int block) {
     p.n_slices = s.recs_base() + s.slices();
     p.n_fed = fed;
     return p;
+}
+
+void partition_streams(const int64_t *n_in, int n_streams, int n_dev, int *owner) {
+    if (n_dev < 1) n_dev = 1;
+    bool equal = true;
+    for (int s = 1; s < n_streams && equal; ++s) equal = n_in[s] == n_in[0];
+    if (equal) {
+        const int base = n_streams / n_dev, extra = n_streams % n_dev;
+        int s = 0;
+        for (int d = 0; d < n_dev; ++d)
+            for (int i = 0; i < base + (d < extra ? 1 : 0); ++i) owner[s++] = d;
+        return;
+    }
+    std::vector<int> order(n_streams);
+    for (int s = 0; s < n_streams; ++s) order[s] = s;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n_in[a] > n_in[b]; });
+    for (int i = 0; i < n_streams; ++i) {
+        const int lap = i / n_dev, pos = i % n_dev;
+        owner[order[i]] = (lap % 2 == 0) ? pos : n_dev - 1 - pos;
+    }
 }
 
 }  // namespace pvgpu

@@ -168,4 +168,9 @@ struct StreamPlan {
 };
 StreamPlan plan_stream(Scheduler &s, long n_in, int block /*0 = CLI default*/);
 
+// Streams -> devices: a stream (all of its channels) shares nothing with any other stream.  Equal-length
+// batches take a contiguous, balanced block partition; ragged batches are sorted by length (longest first, stable) and
+// dealt boustrophedon so that every device gets a similar amount of audio.  owner[s] = index of the device of stream s.
+void partition_streams(const int64_t *n_in, int n_streams, int n_dev, int *owner);
+
 }  // namespace pvgpu

@@ -150,8 +150,13 @@ class PhaseVocoderBatch:
         return n_out
 
     def run_device(self, d_in_ptr: int, in_stride: int, d_out_ptr: int, out_stride: int, cuda_stream: int = 0, fmt=_lib.F32):
+        """Enqueue one run on the caller's CUDA stream (0 = the legacy default stream); never blocks the host."""
         check(_lib.lib().pvgpu_batch_run_device(self._h, C.c_void_p(d_in_ptr), int(in_stride), C.c_void_p(d_out_ptr),
                                                 int(out_stride), fmt, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        """Wait for the last run_device."""
+        check(_lib.lib().pvgpu_batch_synchronize(self._h))
 
     def run_host_rows(self, in_rows, out_rows, fmt=_lib.F32):
         """in_rows / out_rows: lists of numpy arrays (or raw addresses), one per channel row."""
@@ -191,3 +196,99 @@ class PhaseVocoderBatch:
         v = [C.c_int64() for _ in range(4)]
         check(_lib.lib().pvgpu_batch_stats(self._h, *[C.byref(x) for x in v]))
         return dict(kernel_launches=v[0].value, slices=v[1].value, h2d_bytes=v[2].value, d2h_bytes=v[3].value)
+
+
+class PhaseVocoderMultiBatch:
+    """The same batch sharded across several GPUs of one box inside the library (pvgpu_mbatch_*): one host thread and one
+    pvgpu_batch per device, streams partitioned by index, results written straight into the caller's rows."""
+
+    def __init__(self, n_streams, max_in_samples, sampleRate, numChannels, timeratio, pitchshift, mode=NORMAL_SHIFT,
+                 coremode=PHASE_LOCKED, fftsize=2048, hopsize=0, devices=None):
+        self._h = C.c_void_p()
+        self.n_streams, self.channels = int(n_streams), int(numChannels)
+        devs = list(devices) if devices is not None else []
+        arr = (C.c_int * max(len(devs), 1))(*devs)
+        check(_lib.lib().pvgpu_mbatch_create(C.byref(_cfg(sampleRate, numChannels, timeratio, pitchshift, mode, coremode, fftsize,
+                                                           hopsize, 0)), self.n_streams, int(max_in_samples),
+                                             arr if devs else None, len(devs), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().pvgpu_mbatch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def plan(self, n_in, block: int = 0) -> np.ndarray:
+        n_in = np.ascontiguousarray(np.broadcast_to(np.asarray(n_in, dtype=np.int64), (self.n_streams,)))
+        n_out = np.zeros(self.n_streams, dtype=np.int64)
+        p = C.POINTER(C.c_int64)
+        check(_lib.lib().pvgpu_mbatch_plan(self._h, n_in.ctypes.data_as(p), int(block), n_out.ctypes.data_as(p)))
+        self.n_out = n_out
+        return n_out
+
+    def owner(self) -> np.ndarray:
+        o = np.zeros(self.n_streams, dtype=np.int32)
+        check(_lib.lib().pvgpu_mbatch_owner(self._h, o.ctypes.data_as(C.POINTER(C.c_int))))
+        return o
+
+    def run_host_rows(self, in_rows, out_rows, fmt=_lib.F32):
+        n = self.n_streams * self.channels
+        ip, op = (C.c_void_p * n)(), (C.c_void_p * n)()
+        for r in range(n):
+            ip[r] = in_rows[r] if isinstance(in_rows[r], int) else in_rows[r].ctypes.data
+            op[r] = out_rows[r] if isinstance(out_rows[r], int) else out_rows[r].ctypes.data
+        check(_lib.lib().pvgpu_mbatch_run_host(self._h, ip, op, fmt))
+
+    def run(self, streams, fmt=_lib.F32):
+        dt = np.int16 if fmt == _lib.S16 else np.float32
+        xs = [np.ascontiguousarray(x, dtype=dt) for x in streams]
+        assert len(xs) == self.n_streams and all(x.shape[0] == self.channels for x in xs)
+        n_out = self.plan([x.shape[1] for x in xs])
+        outs = [np.zeros((self.channels, int(n_out[s])), dtype=dt) for s in range(self.n_streams)]
+        self.run_host_rows([xs[s][c] for s in range(self.n_streams) for c in range(self.channels)],
+                           [outs[s][c] for s in range(self.n_streams) for c in range(self.channels)], fmt)
+        return outs
+
+    def stats(self) -> dict:
+        v = [C.c_int64() for _ in range(3)]
+        used = C.c_int()
+        check(_lib.lib().pvgpu_mbatch_stats(self._h, *[C.byref(x) for x in v], C.byref(used)))
+        return dict(kernel_launches=v[0].value, h2d_bytes=v[1].value, d2h_bytes=v[2].value, devices_used=used.value)
+
+
+def shard_streams(n_in, n_dev: int) -> np.ndarray:
+    """The library's stream -> device partition (needs no GPU): owner index in [0, n_dev) for every stream."""
+    n_in = np.ascontiguousarray(np.asarray(n_in, dtype=np.int64))
+    owner = np.zeros(n_in.size, dtype=np.int32)
+    check(_lib.lib().pvgpu_shard_streams(n_in.ctypes.data_as(C.POINTER(C.c_int64)), int(n_in.size), int(n_dev),
+                                         owner.ctypes.data_as(C.POINTER(C.c_int))))
+    return owner
+
+
+class HostBuffer:
+    """Page-locked host memory on the NUMA node of a GPU (pvgpu_host_alloc); .array(dtype, shape) views it with numpy."""
+
+    def __init__(self, nbytes: int, device: int = 0, numa_local: bool = True, hugepages: bool = False):
+        self.ptr = C.c_void_p()
+        self.nbytes = int(nbytes)
+        flags = (_lib.HOST_NUMA_LOCAL if numa_local else 0) | (_lib.HOST_HUGEPAGES if hugepages else 0)
+        check(_lib.lib().pvgpu_host_alloc(C.byref(self.ptr), self.nbytes, int(device), flags))
+
+    def array(self, dtype, shape) -> np.ndarray:
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        assert n <= self.nbytes
+        buf = (C.c_char * n).from_address(self.ptr.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def info(self) -> dict:
+        node, huge, nb = C.c_int(), C.c_int(), C.c_size_t()
+        check(_lib.lib().pvgpu_host_info(self.ptr, C.byref(node), C.byref(huge), C.byref(nb)))
+        return dict(numa_node=node.value, hugepages=bool(huge.value), bytes=nb.value)
+
+    def close(self):
+        if getattr(self, "ptr", None) and self.ptr.value:
+            _lib.lib().pvgpu_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+    __del__ = close

@@ -29,6 +29,13 @@ def balanced_partition(lengths: Sequence[int], world: int) -> List[np.ndarray]:
     return [np.array(sorted(s), dtype=np.int64) for s in shards]
 
 
+def library_partition(lengths: Sequence[int], world: int) -> List[np.ndarray]:
+    """The partition libpvgpu.so itself uses for pvgpu_mbatch (pvgpu_shard_streams): per-rank index arrays (sorted)."""
+    from .phasevocoder import shard_streams
+    owner = shard_streams(lengths, world) if len(lengths) else np.zeros(0, np.int32)
+    return [np.flatnonzero(owner == r).astype(np.int64) for r in range(world)]
+
+
 def run_sharded(streams: Sequence[np.ndarray], process_local: Callable[[List[np.ndarray]], List[np.ndarray]], group=None):
     """Every rank holds the full list of host streams (or at least its own shard's entries), processes its shard with
     `process_local` (the GPU batch on that rank) and rank 0 receives all outputs in the original order."""
@@ -36,7 +43,7 @@ def run_sharded(streams: Sequence[np.ndarray], process_local: Callable[[List[np.
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lengths = [int(x.shape[1]) for x in streams]
-    shards = balanced_partition(lengths, world) if len(set(lengths)) > 1 else [np.array(block_partition(len(streams), world, r)) for r in range(world)]
+    shards = library_partition(lengths, world)
     mine = shards[rank]
     local_out = process_local([streams[int(i)] for i in mine]) if len(mine) else []
     if world == 1:

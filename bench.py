@@ -9,8 +9,12 @@
 Workload (config 4 of BASELINE.json): S = 4096 synthetic mono 44.1 kHz streams of 10 s PER GPU, +7 semitones,
 coremode 1 (phase locked), FFT 2048.  A step is one pass of the whole path over that batch.  `value` is measured with
 the inputs resident in HBM (7.2 GB of float32 PCM per GPU, far larger than L2); `e2e` goes through the host-buffer
-entry point (pinned host memory -> H2D -> kernels -> D2H) every step.  Streams are independent, so multi-GPU is one
-process per GPU with its own batch and no collective on the data path (weak scaling).
+entry point (pinned host memory -> H2D -> kernels -> D2H) every step -- int16 PCM rows (the reference CLI's own WAV
+format) lead, float32 rows are reported beside them.  Streams are independent, so multi-GPU is one process per GPU with
+its own batch and no collective on the data path; the default line is weak scaling (4096 streams per GPU) and at N > 1
+carries the strong-scaling figure (4096 streams in total, BASELINE.json configs[3] read literally) beside it.
+After the timed regions a few rows of the batch that was actually timed are compared with the unmodified reference
+(oracle/_ref/pvref_drv on the same samples): `parity` in the JSON line.
 """
 from __future__ import annotations
 
@@ -63,6 +67,12 @@ def parse():
     ap.add_argument("--cpu-streams-per-core", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg at N > 1")
+    ap.add_argument("--no-latency", action="store_true", help="skip the streaming per-call latency leg")
+    ap.add_argument("--parity-rows", type=int, default=4)
+    ap.add_argument("--host-alloc", default="numa", choices=["numa", "numa-huge", "torch"],
+                    help="pinned host buffers of the e2e legs: pvgpu_host_alloc on the GPU's NUMA node (default), the same on explicit 2 MB pages, or torch pin_memory")
     args = ap.parse_args()
     global SR, CHANNELS, TIMERATIO, SEMITONES, MODE, COREMODE, FFT
     SR, CHANNELS, TIMERATIO, SEMITONES, MODE, COREMODE, FFT, default_streams = WORKLOADS[args.workload]
@@ -228,6 +238,77 @@ def make_inputs(torch, dev, streams, n, seed):
     return out
 
 
+def reference_rows(rows_f32):
+    """The unmodified reference (one fresh process per stream) on the given [channels, n] float32 streams; falls back to the
+    C restatement (pinned bit-exactly to it by tests/test_oracle_vs_ref.py) when oracle/_ref was not shipped."""
+    from oracle import pv_oracle as O
+    if O.have_ref():
+        return [O.run_ref(x, SR, timeratio=TIMERATIO, semitones=SEMITONES, mode=MODE, coremode=COREMODE, fftsize=FFT) for x in rows_f32], "reference"
+    return [O.run_offline(x, SR, timeratio=TIMERATIO, semitones=SEMITONES, mode=MODE, coremode=COREMODE, fftsize=FFT) for x in rows_f32], "port"
+
+
+def parity_f32(got, refs):
+    """got / refs: lists of [channels, n] arrays.  counts, worst SNR and max-abs over all channels."""
+    ok, snr_min, mx = True, float("inf"), 0.0
+    for y, r in zip(got, refs):
+        if y.shape != r.shape:
+            ok = False
+            m = min(y.shape[1], r.shape[1])
+            y, r = y[:, :m], r[:, :m]
+        for c in range(r.shape[0]):
+            e = y[c].astype(np.float64) - r[c].astype(np.float64)
+            pw, pe = float(np.sum(r[c].astype(np.float64) ** 2)), float(np.sum(e ** 2))
+            mx = max(mx, float(np.max(np.abs(e))) if e.size else 0.0)
+            if pe > 0 and pw > 0:
+                snr_min = min(snr_min, 10 * np.log10(pw / pe))
+    return {"rows": sum(r.shape[0] for r in refs), "counts_equal": ok, "min_snr_db": None if np.isinf(snr_min) else snr_min, "max_abs": mx}
+
+
+def parity_s16(got, refs):
+    """int16 rows against the reference's float output through its own WAV writer rule (x * 32768, clamp, truncate)."""
+    ok, lsb, exact, total, snr_min = True, 0, 0, 0, float("inf")
+    for y, r in zip(got, refs):
+        want = np.clip(r * np.float32(32768.0), -32768.0, 32767.0).astype(np.int32)
+        if y.shape != want.shape:
+            ok = False
+            m = min(y.shape[1], want.shape[1])
+            y, want = y[:, :m], want[:, :m]
+        d = y.astype(np.int32) - want
+        lsb = max(lsb, int(np.max(np.abs(d))) if d.size else 0)
+        exact += int(np.sum(d == 0))
+        total += d.size
+        for c in range(want.shape[0]):
+            pw, pe = float(np.sum(want[c].astype(np.float64) ** 2)), float(np.sum(d[c].astype(np.float64) ** 2))
+            if pe > 0 and pw > 0:
+                snr_min = min(snr_min, 10 * np.log10(pw / pe))
+    return {"rows": sum(r.shape[0] for r in refs), "counts_equal": ok, "max_lsb": lsb, "exact_frac": exact / max(total, 1),
+            "max_abs": lsb / 32768.0, "min_snr_db": None if np.isinf(snr_min) else snr_min}
+
+
+def stream_latency():
+    """Per-call wall time of the streaming drop-in API (processBlock on the CLI's 480-sample blocks, host buffers, one
+    instance = one audiomod::phasevocoder object): p50 / p99 in ms for three configurations."""
+    import audiomod_b200 as A
+    from audiomod_b200.synth import synth
+    out = {}
+    for name, ch, st, mode in (("cfg4_mono_p7", 1, 7.0, 0), ("cfg1_stereo_p4", 2, 4.0, 0), ("robotic_stereo", 2, 0.0, 6)):
+        x = synth(1, 44100, 3.0, ch)
+        B = 480
+        pv = A.phasevocoder(44100, ch, 1.0, st, mode, 1, 2048)
+        times = []
+        for i in range(0, x.shape[1] - B, B):
+            blk = np.ascontiguousarray(x[:, i:i + B])
+            t0 = time.perf_counter()
+            pv.processBlock(blk)
+            times.append(time.perf_counter() - t0)
+        pv.close()
+        t = np.array(times[20:]) * 1e3
+        out[name] = {"p50": float(np.percentile(t, 50)), "p99": float(np.percentile(t, 99)), "max": float(t.max()), "calls": int(t.size)}
+    out["block_samples"] = 480
+    out["block_ms_of_audio"] = 1e3 * 480 / 44100
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -246,89 +327,251 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from audiomod_b200 import _lib
+    _lib.lib().pvgpu_bind_thread_to_device(local)    # host thread (and its first-touch pages) on the GPU's NUMA node
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x):
+        return reduce(x, dist.ReduceOp.MAX) if world > 1 else x
+
     n = int(round(SR * args.secs))
+    stream = torch.cuda.Stream()      # explicit stream: the batch forks from / joins into the caller's stream, events bracket it
+
+    def make_batch(n_streams):
+        S = n_streams * CHANNELS
+        stride = (n + 3) & ~3
+        d_in = torch.zeros((S, stride), dtype=torch.float32, device=dev)
+        d_in[:, :n] = make_inputs(torch, dev, S, n, 1234 + rank)
+        batch = A.PhaseVocoderBatch(n_streams, n, SR, CHANNELS, TIMERATIO, SEMITONES, MODE, COREMODE, FFT, device=local)
+        if args.frames_per_chunk or args.rows_per_group or args.contexts:
+            batch.tune(args.frames_per_chunk, args.rows_per_group, args.contexts)
+        n_out = batch.plan(n)
+        out_stride = (int(n_out.max()) + 3) & ~3
+        d_out = torch.zeros((S, out_stride), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        return batch, d_in, d_out, stride, out_stride, n_out
+
+    def time_device(batch, d_in, d_out, stride, out_stride, steps, warmup):
+        """K steps on `stream`, inputs resident in HBM, CUDA events on the launching stream, max over ranks (ms per step)."""
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                batch.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), out_stride, stream.cuda_stream)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                batch.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), out_stride, stream.cuda_stream)
+            e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    host_bufs = []
+
+    def host_array(dtype, shape):
+        """page-locked host rows for the e2e legs"""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if args.host_alloc == "torch":
+            t = torch.empty(shape, dtype=torch.int16 if np.dtype(dtype) == np.int16 else torch.float32, pin_memory=True)
+            host_bufs.append(t)
+            return t.numpy()
+        hb = A.HostBuffer(nbytes, local, True, args.host_alloc == "numa-huge")
+        host_bufs.append(hb)
+        return hb.array(dtype, shape)
+
+    def time_host(batch, X, Y, fmt, steps):
+        """K steps through the host-buffer entry point; every step copies its inputs H2D and its results D2H.  Timed with
+        CUDA events on the device clock around the (synchronous) calls, max over ranks."""
+        S = X.shape[0]
+        in_rows = [X[r].ctypes.data for r in range(S)]
+        out_rows = [Y[r].ctypes.data for r in range(S)]
+        batch.run_host_rows(in_rows, out_rows, fmt)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            batch.run_host_rows(in_rows, out_rows, fmt)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, batch.stats()
+
     n_streams = args.streams
-    S = n_streams * CHANNELS          # channel rows
-    stride = (n + 3) & ~3
-    d_in = torch.zeros((S, stride), dtype=torch.float32, device=dev)
-    d_in[:, :n] = make_inputs(torch, dev, S, n, 1234 + rank)
-    batch = A.PhaseVocoderBatch(n_streams, n, SR, CHANNELS, TIMERATIO, SEMITONES, MODE, COREMODE, FFT, device=local)
-    if args.frames_per_chunk or args.rows_per_group or args.contexts:
-        batch.tune(args.frames_per_chunk, args.rows_per_group, args.contexts)
-    n_out = batch.plan(n)
-    out_stride = (int(n_out.max()) + 3) & ~3
-    d_out = torch.zeros((S, out_stride), dtype=torch.float32, device=dev)
+    S = n_streams * CHANNELS
+    batch, d_in, d_out, stride, out_stride, n_out = make_batch(n_streams)
     info = batch.info()
-    stream = torch.cuda.current_stream()
 
-    def step_device():
-        batch.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), out_stride, stream.cuda_stream)
-
-    # ---- device-resident throughput ----
-    for _ in range(args.warmup):
-        step_device()
+    # ---- device-resident throughput (the bench contract's `value`) ----
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            batch.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), out_stride, stream.cuda_stream)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = time_device(batch, d_in, d_out, stride, out_stride, args.steps, 0)
     stats = batch.stats()
     clocks = sampler.summary()
+    audio_sec_per_step = world * n_streams * args.secs
+    value = audio_sec_per_step / (ms_step / 1e3)
+    n_out_min = int(n_out.min())
+    checksum = float(d_out[:, :n_out_min].double().abs().mean().item())
+
+    # rows of THIS batch checked against the reference after the timed regions (first / last / spread in between)
+    pr = sorted(set(int(round(i * (n_streams - 1) / max(args.parity_rows - 1, 1))) for i in range(min(args.parity_rows, n_streams))))
+    parity = None
+    refs = None
+    if not args.no_parity:
+        xin = [d_in[s * CHANNELS:(s + 1) * CHANNELS, :n].cpu().numpy() for s in pr]
+        refs, checker = reference_rows(xin)
+        got = [d_out[s * CHANNELS:(s + 1) * CHANNELS, :int(n_out[s])].cpu().numpy() for s in pr]
+        parity = {"checker": checker + (": oracle/_ref/pvref_drv, one fresh process per stream" if checker == "reference" else ": oracle/pv_oracle.c"),
+                  "streams_checked": pr, "bar": "counts equal, >= 90 dB SNR, max-abs <= 1e-4 per channel",
+                  "device_resident_f32": parity_f32(got, refs)}
+
     # per-kernel CUDA-event times: the same steps once more with one group in flight at a time, so that a kernel's
-    # events bracket only that kernel (with several groups in flight kernels of different groups share the SMs)
+    # events bracket only that kernel (with the stages overlapped kernels of neighbouring chunks share the SMs)
     batch.tune(contexts=1)
-    step_device()
+    with torch.cuda.stream(stream):
+        batch.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), out_stride, stream.cuda_stream)
     torch.cuda.synchronize()
     batch.profile(True)
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pe0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    pe1.record(stream)
+    with torch.cuda.stream(stream):
+        pe0.record(stream)
+        for _ in range(args.steps):
+            batch.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), out_stride, stream.cuda_stream)
+        pe1.record(stream)
     torch.cuda.synchronize()
     ms_serial_step = pe0.elapsed_time(pe1) / args.steps
     ktimes = batch.kernel_times()
     batch.profile(False)
     batch.tune(contexts=args.contexts or 3)
-    ms_step = ms_total / args.steps
-    audio_sec_per_step = world * n_streams * args.secs
-    value = audio_sec_per_step / (ms_step / 1e3)
-    checksum = float(d_out[:, :int(n_out.min())].double().abs().mean().item())
 
-    # ---- roofline of the dominant kernel (staged-traffic model, DESIGN.md "Algorithmic bytes") ----
+    roofline = make_roofline(args, info, stats, ktimes, ms_step, ms_serial_step, S, n, n_out, clocks)
+
+    # ---- end to end through the host-buffer entry point ----
+    e2e = None
+    if not args.no_e2e:
+        # int16 PCM rows: the reference CLI's own I/O format (16-bit WAV in, 16-bit WAV out, main/main.cc:136)
+        q_in, q_out = host_array(np.int16, (S, stride)), host_array(np.int16, (S, out_stride))
+        q_in[:] = torch.round(d_in * 32768.0).clamp_(-32768, 32767).to(torch.int16).cpu().numpy()
+        dt_ms, st = time_host(batch, q_in, q_out, A.S16, args.steps)
+        e2e = {"value": audio_sec_per_step / (dt_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] * world,
+               "d2h_bytes_per_step": st["d2h_bytes"] * world, "ms_per_step": dt_ms,
+               "format": "int16 PCM rows in, int16 PCM rows out (the reference CLI's WAV sample format), page-locked host memory",
+               "host_alloc": args.host_alloc, "result_checksum": float(np.abs(q_out[:, :n_out_min].astype(np.float64)).mean() / 32768.0)}
+        if parity is not None:
+            parity["e2e_s16"] = parity_s16([q_out[s * CHANNELS:(s + 1) * CHANNELS, :int(n_out[s])].copy() for s in pr], refs)
+        del q_in, q_out
+        for hb in host_bufs:
+            if hasattr(hb, "close"):
+                hb.close()
+        host_bufs.clear()
+        # float32 rows beside it (twice the bytes per sample)
+        h_in, h_out = host_array(np.float32, (S, stride)), host_array(np.float32, (S, out_stride))
+        h_in[:] = d_in.cpu().numpy()
+        dt_ms, st = time_host(batch, h_in, h_out, A.F32, args.steps)
+        e2e["f32"] = {"value": audio_sec_per_step / (dt_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] * world,
+                      "d2h_bytes_per_step": st["d2h_bytes"] * world, "ms_per_step": dt_ms,
+                      "format": "float32 rows in, float32 rows out, page-locked host memory",
+                      "result_checksum": float(np.abs(h_out[:, :n_out_min].astype(np.float64)).mean())}
+        if parity is not None:
+            parity["e2e_f32"] = parity_f32([h_out[s * CHANNELS:(s + 1) * CHANNELS, :int(n_out[s])].copy() for s in pr], refs)
+        del h_in, h_out
+        for hb in host_bufs:
+            if hasattr(hb, "close"):
+                hb.close()
+        host_bufs.clear()
+    if parity is not None and world > 1:     # every rank checked its own rows: fold to the worst
+        for leg in [k for k in parity if isinstance(parity[k], dict)]:
+            d = parity[leg]
+            d["counts_equal"] = bool(reduce(1.0 if d["counts_equal"] else 0.0, dist.ReduceOp.MIN) > 0.5)
+            d["max_abs"] = reduce(d["max_abs"], dist.ReduceOp.MAX)
+            d["min_snr_db"] = reduce(d["min_snr_db"] if d["min_snr_db"] is not None else 1e9, dist.ReduceOp.MIN)
+            d["rows"] = int(reduce(float(d["rows"]), dist.ReduceOp.SUM))
+        parity["ranks"] = world
+
+    # ---- strong scaling: the literal configs[3], 4096 streams IN TOTAL sharded over the N GPUs ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        batch.close()
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        per = [len(range(*_block(args.streams, world, r))) for r in range(world)]
+        b2, i2, o2, st2, ost2, no2 = make_batch(per[rank])
+        ms2 = time_device(b2, i2, o2, st2, ost2, args.steps, args.warmup)
+        strong = {"scaling": "strong", "total_streams": args.streams, "streams_per_gpu": per, "ms_per_step": ms2,
+                  "value": args.streams * args.secs / (ms2 / 1e3), "unit": UNIT}
+        if not args.no_e2e:
+            S2 = per[rank] * CHANNELS
+            q_in, q_out = host_array(np.int16, (S2, st2)), host_array(np.int16, (S2, ost2))
+            q_in[:] = torch.round(i2 * 32768.0).clamp_(-32768, 32767).to(torch.int16).cpu().numpy()
+            dt_ms, _ = time_host(b2, q_in, q_out, A.S16, args.steps)
+            strong["e2e"] = {"value": args.streams * args.secs / (dt_ms / 1e3), "unit": UNIT, "ms_per_step": dt_ms, "format": "int16 PCM rows"}
+            del q_in, q_out
+        b2.close()
+    else:
+        batch.close()
+
+    latency = None
+    cpu = None
+    if rank == 0 and world == 1:
+        if not args.no_latency:
+            latency = stream_latency()
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            ncpu = max(cores, cores * args.cpu_streams_per_core)
+            v, kind, dt = cpu_run(ncpu, args.secs, cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": f"{ncpu} streams of the same workload ({args.secs:g} s each, float32 sample files through oracle/_ref/pvref_drv = the "
+                             f"unmodified reference library driven with audiomod-exe's block protocol; no WAV parsing), one OS process per stream, {dt:.1f} s wall"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": stats["kernel_launches"] * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+                "parity": parity, "strong_scaling": strong, "stream_latency_ms": latency, "result_checksum": checksum,
+                "value_definition": "inputs resident in HBM when the timed region starts (bench contract); e2e.value is the SURVEY 8(d) metric "
+                                    "with H2D + kernels + D2H inside the timed region"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _block(n, world, rank):
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def make_roofline(args, info, stats, ktimes, ms_step, ms_serial_step, S, n, n_out, clocks):
+    """Roofline numbers of the step.  `frac` is the HBM fraction of the dominant kernel on the staged-
+    traffic model; the binding resource of this path is not DRAM but instruction issue / the L1 data pipe, so the line also
+    carries issue_frac (warp instructions per frame from the committed ncu capture) and fp32_frac."""
     N, hop, H, half = info["fftsize"], info["hop"], info["bins"], info["fftsize"] // 2
     slices = stats["slices"]
     shift = hop * info["hs_ratio"]
+    P = half / 5.0     # peaks per frame of a noise-like spectrum (strict +-2 local maxima), measured on the synthetic workload
     per_frame = {"analyse": 4 * (hop + 2 * H), "phase_core": 4 * (2 * H + half), "synthesise": 4 * (2 * H + N),
-                 "ola_resample": 4 * (N + shift / info["pitch_scale"])}
-    per_frame["fixed_phase"] = 4 * H
-    # phase-locked core on Cartesian spectra (pv_lock.cuh): P peaks per frame is data dependent; a noise-like spectrum has a
-    # strict +-2 local maximum at one bin in five, which is what the synthetic workload measures (profiles/traffic.json)
-    P = half / 5.0
-    per_frame["lock_peaks"] = 4 * 2 * H * (1 + 1.0 / 32) + 16 * P + 2 * half + 8   # spectrum (+ warm-up frame per run) -> records, map, header
-    per_frame["lock_chain"] = 16 * P + 8 + 8 * P                                  # records, header -> (cos, sin) per region
-    if ktimes.get("lock_chain", (0, 0))[1] > 0:
-        per_frame["synthesise"] = 4 * (2 * H + N) + 2 * half + 8 * P + 8          # + bin->region map, rotations, header
-    dom = max((k for k in per_frame if ktimes.get(k, (0, 0))[1] > 0), key=lambda k: ktimes[k][0])
+                 "ola_resample": 4 * (N + shift / info["pitch_scale"]), "fixed_phase": 4 * H,
+                 "lock_peaks": 4 * 2 * H * (1 + 1.0 / 32) + 16 * P + 2 * half + 8, "lock_chain": 16 * P + 8 + 8 * P,
+                 # fused inverse FFT + overlap-add + resampler: spectrum, bin->region map, rotations in; PCM out; OLA tail per chunk
+                 "synth_ola": 4 * 2 * H + 2 * half + 8 * P + 8 + 4 * shift / info["pitch_scale"] + 2 * 4 * N / 64.0}
+    if ktimes.get("lock_chain", (0, 0))[1] > 0 and ktimes.get("synthesise", (0, 0))[1] > 0:
+        per_frame["synthesise"] = 4 * (2 * H + N) + 2 * half + 8 * P + 8
+    live = [k for k in per_frame if ktimes.get(k, (0, 0))[1] > 0]
+    dom = max(live, key=lambda k: ktimes[k][0])
     dom_ms, dom_launches = ktimes[dom]
     bytes_total = per_frame[dom] * slices * S * args.steps
     achieved = bytes_total / (dom_ms / 1e3) / 1e9
@@ -338,79 +581,38 @@ def main():
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         pass
-    traffic = None
-    try:   # measured DRAM bytes per frame of that kernel from the committed ncu --set full capture, scaled to one launch
+    prof = {}
+    try:   # per-kernel counters of the committed ncu --set full capture (scripts/profile_digest.py)
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f)[dom]["dram_bytes_per_frame"] * slices * S * args.steps / max(dom_launches, 1)
+            prof = json.load(f)
     except Exception:
         pass
+    traffic = prof.get(dom, {}).get("dram_bytes_per_frame")
+    traffic = traffic * slices * S * args.steps / max(dom_launches, 1) if traffic is not None else None
     kernel_ms_sum = sum(v[0] for v in ktimes.values())
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_total / max(dom_launches, 1),
-                "avg_launch_ms": dom_ms / max(dom_launches, 1),
-                "kernel_share_of_step": dom_ms / max(kernel_ms_sum, 1e-9),
-                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
-                "serialised_ms_per_step": ms_serial_step,
-                "compulsory_io_frac": (4.0 * (n + float(n_out.max())) * S) / (ms_step / 1e3) / 1e9 / peak}
-
-    # ---- end to end through the host-buffer entry point ----
-    e2e = None
-    if not args.no_e2e:
-        h_in = torch.empty((S, stride), dtype=torch.float32, pin_memory=True)
-        h_in.copy_(d_in)
-        h_out = torch.empty((S, out_stride), dtype=torch.float32, pin_memory=True)
-        in_rows = [h_in.data_ptr() + 4 * stride * r for r in range(S)]
-        out_rows = [h_out.data_ptr() + 4 * out_stride * r for r in range(S)]
-        batch.run_host_rows(in_rows, out_rows)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            batch.run_host_rows(in_rows, out_rows)
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0) / args.steps
-        st = batch.stats()
-        e2e = {"value": audio_sec_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] * world,
-               "d2h_bytes_per_step": st["d2h_bytes"] * world, "ms_per_step": dt * 1e3, "format": "f32 in, f32 out, pinned host memory",
-               "result_checksum": float(h_out[:, :int(n_out.min())].double().abs().mean().item())}
-
-        # the same through int16 PCM rows (the reference CLI's own I/O format: 16-bit WAV in, 16-bit WAV out), reported beside it
-        del h_in, h_out
-        q_in = torch.empty((S, stride), dtype=torch.int16, pin_memory=True)
-        q_in.copy_(torch.round(d_in * 32768.0).clamp_(-32768, 32767).to(torch.int16))
-        q_out = torch.empty((S, out_stride), dtype=torch.int16, pin_memory=True)
-        qi = [q_in.data_ptr() + 2 * stride * r for r in range(S)]
-        qo = [q_out.data_ptr() + 2 * out_stride * r for r in range(S)]
-        batch.run_host_rows(qi, qo, A.S16)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            batch.run_host_rows(qi, qo, A.S16)
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0) / args.steps
-        st = batch.stats()
-        e2e["s16"] = {"value": audio_sec_per_step / dt, "unit": UNIT, "h2d_bytes_per_step": st["h2d_bytes"] * world,
-                      "d2h_bytes_per_step": st["d2h_bytes"] * world, "ms_per_step": dt * 1e3,
-                      "format": "int16 PCM in, int16 PCM out, pinned host memory"}
-        del q_in, q_out
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        ncpu = max(cores, cores * args.cpu_streams_per_core)
-        v, kind, dt = cpu_run(ncpu, args.secs, cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-               "sample": f"{ncpu} streams of the same workload ({args.secs:g} s each), one OS process per stream, {dt:.1f} s wall"}
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
-                "gpu_launches": stats["kernel_launches"] * args.steps, "roofline": roofline, "cpu_baseline": cpu,
-                "result_checksum": checksum}
-        print(json.dumps(line), flush=True)
-    batch.close()
-    if world > 1:
-        dist.destroy_process_group()
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    frames_per_step = slices * S
+    instr = {k: prof.get(k, {}).get("warp_instr_per_frame") for k in live}
+    issue_frac = None
+    if all(v is not None for v in instr.values()) and instr:
+        issue_frac = sum(instr.values()) * frames_per_step / (148 * 4 * sm_mhz * 1e6) / (ms_step / 1e3)
+    in_samples_per_s = S * n / (ms_step / 1e3)
+    fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6
+    return {"bound": prof.get(dom, {}).get("limiter", "issue slots / L1 data pipe (not DRAM): see issue_frac"), "kernel": dom,
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": bytes_total / max(dom_launches, 1),
+            "avg_launch_ms": dom_ms / max(dom_launches, 1),
+            "kernel_share_of_step": dom_ms / max(kernel_ms_sum, 1e-9),
+            "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items() if v[1]},
+            "serialised_ms_per_step": ms_serial_step,
+            "staged_bytes_per_frame": {k: per_frame[k] for k in live},
+            "step_hbm_frac_staged": sum(per_frame[k] for k in live) * frames_per_step / (ms_step / 1e3) / 1e9 / peak,
+            "compulsory_io_frac": (4.0 * (n + float(n_out.max())) * S) / (ms_step / 1e3) / 1e9 / peak,
+            "issue_frac": issue_frac, "warp_instr_per_frame": instr,
+            "issue_frac_definition": "sum over kernels of warp instructions per frame (committed ncu capture, profiles/traffic.json) x frames per step / "
+                                     "(148 SMs x 4 schedulers x sm_mhz) / step time",
+            "fp32_frac": 2200.0 * in_samples_per_s / fp32_peak,
+            "fp32_frac_definition": "2.2 kflop per input sample (SURVEY 8(d)) x input samples/s / (148 x 128 lanes x 2 x sm_mhz)"}
 
 
 if __name__ == "__main__":

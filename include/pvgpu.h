@@ -16,6 +16,7 @@
 #ifndef PVGPU_H_
 #define PVGPU_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -101,10 +102,13 @@ void pvgpu_batch_destroy(pvgpu_batch *b);
  * block = 0 uses the CLI block size.  Must be called before a run; may be called again. */
 int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_out);
 /* Inputs and outputs resident in device memory: d_in [rows][in_stride], d_out [rows][out_stride]
- * (elements of `fmt`), out_stride >= max n_out.  cuda_stream is a cudaStream_t (NULL = the batch's own
- * stream); the call only enqueues work and does not synchronise when a stream is given. */
+ * (elements of `fmt`), out_stride >= max n_out.  cuda_stream is the caller's cudaStream_t, with CUDA's own convention
+ * that NULL is the legacy default stream: the run is ordered after everything queued on that stream before the call and
+ * before everything queued on it afterwards.  The call only enqueues work and never blocks the host;
+ * pvgpu_batch_synchronize waits for the last run. */
 int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt,
                            void *cuda_stream);
+int pvgpu_batch_synchronize(pvgpu_batch *b);
 /* Host buffers (pinned or pageable): one pointer per row; copies in, runs, copies out, synchronises.
  * Stream groups are pipelined so H2D, kernels and D2H overlap. */
 int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt);
@@ -112,7 +116,8 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
 int pvgpu_batch_stats(const pvgpu_batch *b, int64_t *kernel_launches, int64_t *slices, int64_t *h2d_bytes, int64_t *d2h_bytes);
 int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);
 /* Per-kernel device timing with CUDA events recorded on the launching stream around every launch.  kinds:
- * 0 analyse, 1 phase core, 2 synthesise, 3 overlap-add + resample, 5 fixed phase (robotic/whisper).
+ * 0 analyse, 1 phase core (polar), 2 synthesise, 3 overlap-add + resample, 5 fixed phase (robotic/whisper on polar spectra),
+ * 6 lock_peaks, 7 lock_chain (phase-locked core on Cartesian spectra).
  * pvgpu_batch_kernel_times synchronises the device and returns the totals since profiling was enabled. */
 enum { PVGPU_KINDS = 8 };
 int pvgpu_batch_profile(pvgpu_batch *b, int enable);
@@ -121,6 +126,38 @@ int pvgpu_batch_kernel_times(pvgpu_batch *b, double *ms /*[PVGPU_KINDS]*/, int64
  * and equal-length batches in evenly spaced host rows are pipelined along time; an explicit value selects pipelining
  * across row groups); how many row groups are in flight at once (1..4; each has its own stream, workspace and staging) */
 int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, int contexts);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU batch: the same streams sharded across several devices of one box (BASELINE.json configs[3]: "4096 streams
+ * ... sharded across 1/2/4/8 B200").  Nothing like it exists in the reference (one thread, no device).
+ * A stream (all of its channels) shares nothing with any other stream, so there is no collective: the library partitions
+ * the streams (equal lengths: contiguous balanced blocks; ragged: longest first, dealt boustrophedon), runs one
+ * pvgpu_batch per device from one host thread per device, and every device's D2H copies land directly in the caller's
+ * row pointers -- the "host-side gather".  Results are bit-identical to a single-device run.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pvgpu_mbatch pvgpu_mbatch;
+/* devices == NULL (or n_dev <= 0): every visible device.  cfg->device is ignored. */
+int pvgpu_mbatch_create(const pvgpu_config *cfg, int n_streams, int64_t max_in_samples, const int *devices, int n_dev, pvgpu_mbatch **out);
+void pvgpu_mbatch_destroy(pvgpu_mbatch *m);
+int pvgpu_mbatch_plan(pvgpu_mbatch *m, const int64_t *n_in, int block, int64_t *n_out);
+/* rows in the caller's stream order: row = stream * channels + channel, exactly like pvgpu_batch_run_host */
+int pvgpu_mbatch_run_host(pvgpu_mbatch *m, const void *const *in_rows, void *const *out_rows, int fmt);
+int pvgpu_mbatch_stats(const pvgpu_mbatch *m, int64_t *kernel_launches, int64_t *h2d_bytes, int64_t *d2h_bytes, int *devices_used);
+/* CUDA device ordinal that processes each stream (after pvgpu_mbatch_plan) */
+int pvgpu_mbatch_owner(const pvgpu_mbatch *m, int *owner_device /*[n_streams]*/);
+/* the partition rule on its own (needs no GPU): owner[s] in [0, n_dev) */
+int pvgpu_shard_streams(const int64_t *n_in, int n_streams, int n_dev, int *owner);
+
+/* Page-locked host buffers for batch I/O, placed on the NUMA node of `device` (a B200 box has two CPU sockets; pinned
+ * pages on the far socket cross the inter-socket link and halve the copy rate once all eight GPUs move data).  flags: */
+enum { PVGPU_HOST_NUMA_LOCAL = 1, PVGPU_HOST_HUGEPAGES = 2 /* explicit 2 MB pages (MAP_HUGETLB) when the box has a pool; else THP */ };
+int pvgpu_host_alloc(void **ptr, size_t bytes, int device, int flags);
+int pvgpu_host_free(void *ptr);
+/* where a buffer ended up: node it was bound to (-1: not bound), whether explicit huge pages were granted, mapped bytes */
+int pvgpu_host_info(const void *ptr, int *numa_node, int *hugepages, size_t *bytes);
+/* NUMA node of a CUDA device from sysfs (-1 when unknown); pin the calling thread to that node's cores */
+int pvgpu_device_numa_node(int device);
+int pvgpu_bind_thread_to_device(int device);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage hooks for the parity tests (tests/ compares each stage with the CPU oracle).  Device work,

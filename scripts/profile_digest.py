@@ -11,7 +11,7 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src, dst = os.path.join(root, "gpurun_out"), os.path.join(root, "profiles")
 for name in (f"{tag}_bench.log", f"{tag}_launches.csv", f"{tag}_ncu_full_raw.csv"):
     shutil.copy(os.path.join(src, name), os.path.join(dst, name))
-KIND = {"k_analyse": "analyse", "k_lock_peaks": "lock_peaks", "k_lock_chain": "lock_chain", "k_synthesise": "synthesise",
+KIND = {"k_synth_ola": "synth_ola", "k_analyse": "analyse", "k_lock_peaks": "lock_peaks", "k_lock_chain": "lock_chain", "k_synthesise": "synthesise",
         "k_ola_resample": "ola_resample", "k_phase_lock": "phase_core", "k_phase_core": "phase_core"}
 data = list(csv.reader(open(os.path.join(src, f"{tag}_ncu_full_raw.csv"))))
 hdr = data[0]
@@ -27,7 +27,10 @@ for r in data[2:]:
     rd = f("dram__bytes_read.sum") * scale.get(unit.get("dram__bytes_read.sum"), 1.0)
     wr = f("dram__bytes_write.sum") * scale.get(unit.get("dram__bytes_write.sum"), 1.0)
     n = rows * frames
-    traffic[kind] = {"dram_bytes_per_frame": (rd + wr) / n,
+    issue, pipe = f("smsp__issue_active.avg.pct_of_peak_sustained_active"), f("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")
+    traffic[kind] = {"dram_bytes_per_frame": (rd + wr) / n, "warp_instr_per_frame": f("smsp__inst_executed.sum") / n,
+                     "issue_active_pct": issue, "l1_data_pipe_pct": pipe,
+                     "limiter": "latency (serial chain)" if kind == "lock_chain" else ("l1_data_pipe" if pipe == pipe and pipe > issue else "issue"),
                      "source": f"profiles/{tag}_ncu_full_raw.csv (ncu --set full, {rows} rows x {frames} frames per launch)"}
     table.append((kind, f("gpu__time_duration.sum"), f("smsp__inst_executed.sum") / n, f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                   f("sm__warps_active.avg.pct_of_peak_sustained_active"), (rd + wr) / n, f("launch__registers_per_thread"),

@@ -57,3 +57,18 @@ def test_partitions_cover_and_balance():
     assert sorted(np.concatenate(shards).tolist()) == list(range(101))
     tot = [int(lens[s].sum()) for s in shards]
     assert max(tot) / min(tot) < 1.1
+
+
+def test_library_partition_matches_python_rule(pvlib):
+    """pvgpu_shard_streams (what pvgpu_mbatch uses on the device side) == the documented rule of shard.py."""
+    from audiomod_b200.shard import balanced_partition, block_partition, library_partition
+    rng = np.random.default_rng(2)
+    for n, w in ((4096, 8), (4097, 8), (5, 8), (7, 2), (1, 1)):
+        got = library_partition([441000] * n, w)
+        assert [g.tolist() for g in got] == [list(block_partition(n, w, r)) for r in range(w)]
+    for n, w in ((101, 4), (9, 8), (64, 3)):
+        lens = rng.integers(1000, 500000, size=n)
+        lens[::7] = lens[0]                      # ties keep the stable order
+        got = library_partition(lens, w)
+        want = balanced_partition(lens, w)
+        assert [g.tolist() for g in got] == [x.tolist() for x in want]

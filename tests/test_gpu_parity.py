@@ -336,15 +336,25 @@ def test_device_resident_entry_point(A, oracle):
     b = A.PhaseVocoderBatch(S, n, sr, 1, 1.0, 7.0)
     n_out = b.plan(n)
     stride, ostride = (n + 3) & ~3, (int(n_out.max()) + 3) & ~3
-    d_in = torch.zeros((S, stride), dtype=torch.float32, device="cuda")
-    d_in[:, :n] = torch.from_numpy(np.concatenate(xs, axis=0)).cuda()
-    d_out = torch.full((S, ostride), 7.0, dtype=torch.float32, device="cuda")
-    b.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), ostride, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    y = d_out.cpu().numpy()
+    ref = [oracle.run_offline(x, sr, semitones=7.0) for x in xs]
+    host = torch.from_numpy(np.concatenate(xs, axis=0)).pin_memory()
+    # (a) the legacy default stream (handle 0, what torch.cuda.current_stream() is by default), (b) an explicit non-blocking
+    # stream: in both the fill kernels queued just before the call and the read-back queued just after it must be ordered
+    # around the run without any host synchronisation in between (the null handle used to mean "own stream")
+    for st in (torch.cuda.current_stream(), torch.cuda.Stream()):
+        with torch.cuda.stream(st):
+            d_in = torch.zeros((S, stride), dtype=torch.float32, device="cuda")
+            d_out = torch.full((S, ostride), 7.0, dtype=torch.float32, device="cuda")
+            d_in[:, :n].copy_(host, non_blocking=True)
+            b.run_device(d_in.data_ptr(), stride, d_out.data_ptr(), ostride, st.cuda_stream)
+            y_dev = d_out.clone()           # same stream, after the run
+            d_in.zero_()                    # would corrupt the run if it were not ordered after it
+        b.synchronize()
+        st.synchronize()
+        y = y_dev.cpu().numpy()
+        for i in range(S):
+            assert_parity(y[i:i + 1, :int(n_out[i])], ref[i], f"dev[{i}]")
     b.close()
-    for i in range(S):
-        assert_parity(y[i:i + 1, :int(n_out[i])], oracle.run_offline(xs[i], sr, semitones=7.0), f"dev[{i}]")
 
 
 # ---------------------------------------------------------------------------------------------------------------
