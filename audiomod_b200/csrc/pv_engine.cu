@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -102,6 +103,10 @@ struct Pipeline {
     int max_consumed = 1;   // largest per-slice contribution to the normalised stream seen so far
     int max_out = 1;        // largest per-slice output count seen so far
     int ola_run = 16;       // slices per CTA of k_ola_resample (upper bound)
+    // fused inverse FFT + overlap-add + resampler (pv_fused.cu) instead of k_synthesise_t -> frame ring -> k_ola_resample
+    bool fused = false;
+    bool allow_fused = true;    // PVGPU_FUSED=0 or pvgpu_batch_tune / pvgpu_tune_stream select the split kernels (A/B runs, tests)
+    FusedArgs fa{};             // run / ring / window shape; per-launch fields are filled in run_synth_ola
     // host copy of the uploaded records + the resampler work lists built from them (ResampleRun, pv_kernels.cuh)
     std::vector<SliceRec> h_recs;
     DevBuf b_runs, b_rsent, b_rsfrac;
@@ -432,8 +437,34 @@ struct Pipeline {
         } else if (!d.vocoder && !d.constant_mode) {
             sp = span_begin(1, st); launch_phase_core(p, g, d.cfg.coremode, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches;
         }
+        if (fused) return PVGPU_OK;   // the inverse FFT is part of run_synth_ola
         sp = span_begin(2, st);
         launch_synthesise(p, g, d.vocoder ? b_carmag.as<float>() : nullptr, d.vocoder ? b_carph.as<float>() : nullptr, k0, nf, st);
+        span_end(sp, st); ++launches;
+        return PVGPU_OK;
+    }
+    // Decide whether launches of `frames_per_chunk` frames use the fused kernel, and its shape.  max_shift bounds the
+    // per-slice accumulator advance (and so the resampler's per-slice input).
+    bool plan_fused(int frames_per_chunk, int max_shift, int max_out_bound) {
+        fused = false;
+        const char *env = std::getenv("PVGPU_FUSED");
+        if (!allow_fused || (env && env[0] == '0')) return false;
+        if (fused_frames_in_flight(p.N) == 0) return false;
+        FusedArgs a{};
+        if (!fused_plan(p, frames_per_chunk, max_shift, max_shift, max_out_bound, (size_t)200 * 1024, &a)) return false;
+        fa = a;
+        fused = true;
+        return true;
+    }
+    int run_synth_ola(const DevRows &g, long k0, int nf, cudaStream_t st) {
+        FusedArgs a = fa;
+        a.recs = b_recs.as<SliceRec>(); a.recs_base = recs_base;
+        a.norm = b_norm.as<float>(); a.norm_base = norm_base;
+        a.k0 = k0; a.nf = nf;
+        a.runs = b_runs.as<ResampleRun>(); a.rs_ent = b_rsent.as<unsigned>(); a.rs_frac = b_rsfrac.as<float>(); a.run_origin = run_origin;
+        a.car_mag = d.vocoder ? b_carmag.as<float>() : nullptr; a.car_phase = d.vocoder ? b_carph.as<float>() : nullptr;
+        Span *sp = span_begin(4, st);
+        CU(launch_synth_ola(p, g, a, st));
         span_end(sp, st); ++launches;
         return PVGPU_OK;
     }
@@ -448,6 +479,7 @@ struct Pipeline {
         run_analyse(g, k0, nf, st);
         int rc = run_modify_synth(g, k0, nf, st);
         if (rc) return rc;
+        if (fused) return run_synth_ola(g, k0, nf, st);
         run_ola(g, k0, nf, st);
         return PVGPU_OK;
     }
@@ -457,6 +489,8 @@ struct Pipeline {
 struct Workspace {
     DevBuf mag, phase, frames, prev_phase, prev_out, peaks, first, n_in, n_out;
     DevBuf lock_hdr, lock_rec, lock_map, lock_csn, lock_tail, lock_kind, lock_rot;   // phase-locked core on Cartesian spectra
+    DevBuf ola_tail, res_hist;                                                       // fused kernel: per-row carry between launches
+    size_t lock_slots = 0;     // (row, frame) slots per lock buffer set; nbuf sets are allocated when the fused pipeline overlaps stages
     int rows = 0, F = 0, Fr = 0;
 
     // halo: frames before the current chunk that the overlap-add of the chunk (and of the resampler history before
@@ -472,13 +506,21 @@ struct Workspace {
         spec_stride = (size_t)rows * F * p.Hp;
         CU(mag.ensure(sizeof(float) * spec_stride * nbuf));
         CU(phase.ensure(sizeof(float) * spec_stride * nbuf));
-        CU(frames.ensure(sizeof(float) * (size_t)rows * Fr * p.N));
+        if (!pl.fused) CU(frames.ensure(sizeof(float) * (size_t)rows * Fr * p.N));   // the fused kernel keeps the overlap-add on chip
+        else {
+            CU(ola_tail.ensure(sizeof(float) * (size_t)rows * p.N));
+            CU(res_hist.ensure(sizeof(float) * (size_t)rows * std::max(pl.fa.hist_len, 1)));
+        }
         CU(prev_phase.ensure(sizeof(float) * (size_t)rows * p.half));
         CU(prev_out.ensure(sizeof(float) * (size_t)rows * p.half));
         CU(peaks.ensure(sizeof(int) * (size_t)streams * (1 + pl.max_peaks())));
         CU(first.ensure(sizeof(int) * (size_t)streams));
         if (pl.cartesian() && pl.cartesian_lock()) {
-            const size_t slots = (size_t)rows * F, mp = (size_t)pl.max_peaks();
+            // the fused pipeline reads a chunk's lock tables on the overlap-add stream while the next chunk's are being
+            // written: one set per spectra buffer
+            const size_t sets = pl.fused ? (size_t)nbuf : 1;
+            const size_t slots = (size_t)rows * F * sets, mp = (size_t)pl.max_peaks();
+            lock_slots = (size_t)rows * F;
             CU(lock_hdr.ensure(sizeof(int2) * slots));
             CU(lock_rec.ensure(sizeof(float4) * slots * lock_rec_stride(p, (int)mp) + sizeof(float4) * 256));
             CU(lock_map.ensure(sizeof(unsigned short) * slots * p.half));
@@ -501,6 +543,10 @@ struct Workspace {
             CU(cudaMemsetAsync(lock_kind.p, 0, sizeof(int) * (size_t)rows, st));
             CU(cudaMemsetAsync(lock_rot.p, 0, sizeof(float) * (size_t)rows * pl.max_peaks(), st));
         }
+        if (pl.fused) {   // empty accumulator, zero history (speex mem is zero-initialised)
+            CU(cudaMemsetAsync(ola_tail.p, 0, sizeof(float) * (size_t)rows * p.N, st));
+            CU(cudaMemsetAsync(res_hist.p, 0, sizeof(float) * (size_t)rows * std::max(pl.fa.hist_len, 1), st));
+        }
         return PVGPU_OK;
     }
 
@@ -509,8 +555,11 @@ struct Workspace {
         g.frames = frames.as<float>(); g.Fr = Fr;
         g.prev_phase = prev_phase.as<float>(); g.prev_out = prev_out.as<float>();
         g.peaks = peaks.as<int>(); g.maxpk = pl.max_peaks(); g.started = first.as<int>();
-        g.lock_hdr = lock_hdr.as<int2>(); g.lock_rec = lock_rec.as<float4>(); g.rec_stride = lock_rec_stride(pl.p, pl.max_peaks());
-        g.lock_map = lock_map.as<unsigned short>(); g.lock_csn = lock_csn.as<float2>(); g.lock_tail = lock_tail.as<float>();
+        const size_t ls = pl.fused ? lock_slots * (size_t)buf : 0;   // this chunk's set of lock tables
+        g.rec_stride = lock_rec_stride(pl.p, pl.max_peaks());
+        g.lock_hdr = lock_hdr.as<int2>() + ls; g.lock_rec = lock_rec.as<float4>() + ls * g.rec_stride;
+        g.lock_map = lock_map.as<unsigned short>() + ls * pl.p.half; g.lock_csn = lock_csn.as<float2>() + ls * pl.max_peaks(); g.lock_tail = lock_tail.as<float>();
+        g.ola_tail = ola_tail.as<float>(); g.res_hist = res_hist.as<float>();
         g.lock_kind = lock_kind.as<int>(); g.lock_rot = lock_rot.as<float>();
     }
 };
@@ -582,17 +631,22 @@ struct pvgpu_batch {
     bool time_sliced = true;
     // stage overlap needs more than one context's worth of streams; contexts == 1 means strictly serial kernels (profiling)
     bool overlap_stages() const { return n_contexts > 1; }
-    size_t max_ws_bytes = (size_t)24 << 30;   // largest workspace a single group may take
+    size_t max_ws_bytes = (size_t)24 << 30;   // largest workspace a single group may take: a third of the device's free memory at plan time
     size_t ws_bytes_per_row() const {
-        size_t b = sizeof(float) * ((size_t)4 * frames_per_chunk * pl.p.Hp + (size_t)(2 * frames_per_chunk + halo) * pl.p.N + 2 * (size_t)pl.p.half);
+        size_t b = sizeof(float) * ((size_t)4 * frames_per_chunk * pl.p.Hp + 2 * (size_t)pl.p.half);
+        b += pl.fused ? sizeof(float) * ((size_t)pl.p.N + pl.fa.hist_len) : sizeof(float) * (size_t)(2 * frames_per_chunk + halo) * pl.p.N;
         if (pl.cartesian() && pl.cartesian_lock())   // records, bin->region maps and rotations of k_lock_peaks / k_lock_chain
-            b += (size_t)frames_per_chunk * (16 * (size_t)lock_rec_stride(pl.p, pl.max_peaks()) + 2 * (size_t)pl.p.half + 8 * (size_t)pl.max_peaks() + 8);
+            b += (pl.fused ? 2 : 1) * (size_t)frames_per_chunk * (16 * (size_t)lock_rec_stride(pl.p, pl.max_peaks()) + 2 * (size_t)pl.p.half + 8 * (size_t)pl.max_peaks() + 8);
         return b;
     }
     int run_for_chunk = 0;   // frames_per_chunk the resampler work lists were built for
     int prepare_runs() {
         if (run_for_chunk == frames_per_chunk) return PVGPU_OK;
-        int run = ola_run_limit(pl.p, pl.ola_run, pl.max_consumed, pl.max_out);
+        pl.plan_fused(frames_per_chunk, pl.max_consumed, pl.max_out);   // shape of the fused kernel for this chunk size (or the split kernels)
+        if (!pl.fused && halo + pl.ola_run > 90) pl.ola_run = std::max(1, 90 - halo);
+        if (!pl.fused && halo + pl.ola_run > 90)
+            return fail(PVGPU_EINVAL, "stretch/pitch ratio too extreme for the split kernels: %d overlapping frames (the fused kernel has no such limit)", halo);
+        int run = pl.fused ? pl.fa.run : ola_run_limit(pl.p, pl.ola_run, pl.max_consumed, pl.max_out);
         while (run > 1 && frames_per_chunk % run) --run;   // chunks must start on run boundaries
         int rc = pl.build_resample_runs(0, n_slices, run, stream);
         if (rc) return rc;
@@ -603,6 +657,7 @@ struct pvgpu_batch {
         const int C = cfg.channels, total = n_streams * C;
         int group = rows_per_group;
         if (group <= 0) group = (size_t)total * ws_bytes_per_row() <= max_ws_bytes ? total : 1024;   // widest launches that fit
+        group = std::min(group, 65535);   // several kernels put rows (or streams) on grid.y
         group = std::max(C, (group / C) * C);
         return std::min(group, total);
     }
@@ -612,6 +667,8 @@ struct pvgpu_batch {
 //   A  analysis of chunk c            (needs the spectra buffer c%2 free: synthesis of chunk c-2 done)
 //   B  phase core + synthesis of c    (needs A(c); its ring slots free: overlap-add of chunk c-2 done)
 //   C  overlap-add + resampler of c   (needs B(c))
+// With the fused kernel B is the phase core alone and C is inverse FFT + overlap-add + resampler; the spectra and the lock
+// tables of chunk c are then read by C(c), so A(c+2) and B(c+2) wait for C(c) (the wait on ev_ola below covers both).
 // so the latency-bound, serial-in-time phase kernel shares the SMs with the FFT-heavy kernels of its neighbours.
 // before(ci, k0, nf, stA) is called before the analysis of a chunk is enqueued on stA (e.g. to make it wait for an H2D
 // copy), after(ci, k0, nf, stC) once the chunk's overlap-add has been enqueued on stC (e.g. to start a D2H copy).
@@ -633,7 +690,8 @@ static int run_chunks(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, DevRows g, bool ove
         ctx.ws.bind(pl, g, overlap ? (int)(ci & 1) : 0);
         int rc = before(ci, k0, nf, sa);
         if (rc) return rc;
-        if (overlap && ci >= 2) CU(cudaStreamWaitEvent(sa, ctx.ev_syn[e2], 0));
+        // the spectra buffer of chunk ci-2 is free once its inverse FFTs are done (split: stage B; fused: stage C)
+        if (overlap && ci >= 2) CU(cudaStreamWaitEvent(sa, pl.fused ? ctx.ev_ola[e2] : ctx.ev_syn[e2], 0));
         pl.run_analyse(g, k0, nf, sa);
         if (overlap) {
             CU(cudaEventRecord(ctx.ev_an[e], sa));
@@ -645,7 +703,8 @@ static int run_chunks(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, DevRows g, bool ove
             CU(cudaEventRecord(ctx.ev_syn[e], sb));
             CU(cudaStreamWaitEvent(sc, ctx.ev_syn[e], 0));
         }
-        pl.run_ola(g, k0, nf, sc);
+        if (pl.fused) { if ((rc = pl.run_synth_ola(g, k0, nf, sc))) return rc; }
+        else pl.run_ola(g, k0, nf, sc);
         if (overlap) CU(cudaEventRecord(ctx.ev_ola[e], sc));
         if ((rc = after(ci, k0, nf, sc))) return rc;
     }
@@ -756,9 +815,16 @@ int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info) {
 
 int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, int contexts) {
     if (!b) return fail(PVGPU_EINVAL, "null batch");
-    if (frames_per_chunk > 0) b->frames_per_chunk = frames_per_chunk;
+    if (frames_per_chunk > 0 && frames_per_chunk != b->frames_per_chunk) { b->frames_per_chunk = frames_per_chunk; b->run_for_chunk = 0; }
     if (rows_per_group > 0) { b->rows_per_group = rows_per_group; b->time_sliced = false; }   // explicit row groups pipeline across rows instead of time
     if (contexts > 0) b->n_contexts = std::min(contexts, (int)pvgpu_batch::kCtx);
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_set_fused(pvgpu_batch *b, int enable) {
+    if (!b) return fail(PVGPU_EINVAL, "null batch");
+    b->pl.allow_fused = enable != 0;
+    b->run_for_chunk = 0;   // re-plan the launches at the next run
     return PVGPU_OK;
 }
 
@@ -793,8 +859,6 @@ int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_
     b->res_total = main_sched.res_total();
     b->out_total = main_sched.total_out();
     b->halo = halo_of(main_sched.recs(), main_sched.recs_base(), pl.p.rs_active ? (int)pl.p.rs_filt_len : 1);
-    if (b->halo + pl.ola_run > 90) pl.ola_run = std::max(1, 90 - b->halo);
-    if (b->halo + pl.ola_run > 90) return fail(PVGPU_EINVAL, "stretch/pitch ratio too extreme: %d overlapping frames", b->halo);
     int rc;
     if ((rc = pl.upload_schedule(main_sched, nullptr))) return rc;
     if (pl.d.whisper && (rc = pl.build_whisper(b->n_slices))) return rc;
@@ -824,6 +888,11 @@ int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_
         CU(cudaDeviceSynchronize());
     }
     CU(cudaDeviceSynchronize());
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) b->max_ws_bytes = std::max<size_t>((size_t)2 << 30, free_b / 3);
+        else cudaGetLastError();
+    }
     b->run_for_chunk = 0;
     if ((rc = b->prepare_runs())) return rc;
     b->planned = true;
@@ -845,13 +914,13 @@ static int drain_after_error(pvgpu_batch *b, int rc) {
 static int batch_run_device_impl(pvgpu_batch *b, const void *d_in, int64_t in_stride, void *d_out, int64_t out_stride, int fmt, cudaStream_t st) {
     const size_t esz = fmt == PVGPU_S16 ? sizeof(short) : sizeof(float);
     const int total_rows = b->n_streams * b->cfg.channels;
+    int rc;
+    if ((rc = b->prepare_runs())) return rc;   // also decides fused / split, which the workspace layout depends on
     const int group = b->group_rows();
     const int n_groups = (total_rows + group - 1) / group;
     const int n_ctx = std::min(n_groups, b->n_contexts);
-    int rc;
     for (int i = 0; i < n_ctx; ++i)
         if ((rc = b->ctx[i].ws.ensure(b->pl, group, b->frames_per_chunk, b->halo, b->overlap_stages() ? 2 : 1))) return rc;
-    if ((rc = b->prepare_runs())) return rc;
     b->pl.launches = 0;
     // fork: the contexts start after everything already queued on the caller's stream
     CU(cudaEventRecord(b->ev_fork, st));
@@ -1005,7 +1074,7 @@ static int batch_run_host_impl(pvgpu_batch *b, const void *const *in_rows, void 
         bool uniform = b->n_slices > 0 && b->n_in[0] > 0 && b->n_out[0] > 0;
         for (int s = 1; s < b->n_streams && uniform; ++s) uniform = b->n_in[s] == b->n_in[0] && b->n_out[s] == b->n_out[0];
         const ptrdiff_t ip = regular_pitch(in_rows, total_rows), op = regular_pitch((const void *const *)out_rows, total_rows);
-        const bool fits = (size_t)total_rows * b->ws_bytes_per_row() <= b->max_ws_bytes;
+        const bool fits = (size_t)total_rows * b->ws_bytes_per_row() <= b->max_ws_bytes && total_rows <= 65535;
         if (uniform && fits && b->time_sliced && (total_rows == 1 || (ip >= (ptrdiff_t)(b->n_in[0] * esz) && op >= (ptrdiff_t)(b->n_out[0] * esz))))
             return run_host_timesliced(b, in_rows, out_rows, fmt, esz, in_stride, out_stride, ip, op);
     }
@@ -1203,13 +1272,13 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     CU(cudaMemcpyAsync(s->d_len.p, lim.data(), sizeof(int64_t) * lim.size(), cudaMemcpyHostToDevice, s->st));
     int rc;
     if ((rc = pl.upload_schedule(sc, s->st))) return rc;
-    if ((rc = pl.build_resample_runs(k0, k0 + added, ola_run_limit(p, 8, pl.max_consumed, pl.max_out), s->st))) return rc;
+    if ((rc = pl.build_resample_runs(k0, k0 + added, pl.fused ? pl.fa.run : ola_run_limit(p, 8, pl.max_consumed, pl.max_out), s->st))) return rc;
     const SliceRec &first = sc.recs()[k0 - sc.recs_base()];
     const int64_t out_base = first.out_off;
     const int64_t new_out = sc.total_out() - out_base;
     const int64_t out_stride = std::max<int64_t>((new_out + 3) & ~(int64_t)3, 4);
     CU(s->d_out.ensure(sizeof(float) * (size_t)C * out_stride));
-    if (halo_of(sc.recs(), sc.recs_base(), p.rs_active ? (int)p.rs_filt_len : 1) > s->ws.Fr - s->ws.F) return fail(PVGPU_ESTATE, "too many overlapping (dropped) slices; retrieve output more often");
+    if (!pl.fused && halo_of(sc.recs(), sc.recs_base(), p.rs_active ? (int)p.rs_filt_len : 1) > s->ws.Fr - s->ws.F) return fail(PVGPU_ESTATE, "too many overlapping (dropped) slices; retrieve output more often");
     DevRows g{};
     g.rows = C; g.channels = C;
     g.in = s->d_in.as<float>(); g.in_stride = in_stride; g.in_base = s->in_base;
@@ -1284,6 +1353,15 @@ int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out) {
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     const int halo = 80;
     s->pl.ola_run = 8;
+    {   // fused kernel shape from bounds that hold for the whole stream: the increment is clamped to twice its nominal value
+        // (phasevocoderprocess.cc:392-397); robotic / whisper / vocoder / constant / integer ratios advance by a fixed amount
+        const Derived &d = s->pl.d;
+        const bool fixed = d.robotic || d.whisper || d.vocoder || d.constant_mode || d.int_ratio;
+        const int nominal = fixed ? (d.int_ratio && !(d.robotic || d.whisper || d.vocoder || d.constant_mode) ? (int)(size_t)(d.hop * d.hs) : d.hop)
+                                  : (int)std::lrint(2.0 * d.hop * (double)d.hs) + 2;
+        const int out_bound = (int)std::ceil(nominal * (double)(s->pl.p.rs_active ? d.rs.ratio : 1.f)) + 2;
+        s->pl.plan_fused(pvgpu_stream::kF, std::max(nominal, 1), out_bound);
+    }
     if ((rc = s->ws.ensure(s->pl, cfg->channels, pvgpu_stream::kF, halo))) return rc;
     if ((rc = s->ws.reset_state(s->pl, s->st))) return rc;
     *out = s.release();

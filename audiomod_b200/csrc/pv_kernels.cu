@@ -20,27 +20,13 @@
 #include "pv_kernels.cuh"
 #include "pv_fft.cuh"
 #include "pv_math.cuh"
+#include "pv_synth.cuh"
+#include "pv_resample.cuh"
 
 // out-of-line copy of the general atan2f for the rare arguments the fast path rejects (keeps the hot kernels small)
 __device__ __noinline__ float pv_atan2f_rare(float y, float x) { return pv_atan2f(y, x); }
 
 namespace pvgpu {
-
-// PCM sample formats at the batch boundary.  int16 follows the reference's WAV reader / writer: in = (float)(s * (1.0/32768))
-// (main/wavfile.cc:733-752, exact in float), out = (short)(int)clamp(x * 32768.f, -32768, 32767), truncating toward zero
-// (wavfile.cc:1294-1306, 1508-1526).
-__device__ __forceinline__ float pcm_load(const void *base, int fmt, int64_t idx) {
-    return fmt ? (float)((const short *)base)[idx] * (1.0f / 32768.0f) : ((const float *)base)[idx];
-}
-__device__ __forceinline__ void pcm_store(void *base, int fmt, int64_t idx, float v) {
-    if (fmt) {
-        float s = __fmul_rn(v, 32768.0f);
-        s = s > 32767.0f ? 32767.0f : (s < -32768.0f ? -32768.0f : s);
-        ((short *)base)[idx] = (short)(int)s;
-    } else {
-        ((float *)base)[idx] = v;
-    }
-}
 
 // All butterfly stages of the nc-point complex FFT, in place in shared memory (data already permuted).
 template <bool kInverse>
@@ -738,73 +724,6 @@ __global__ void k_synthesise(const DevPlan p, const DevRows g, const float *__re
 // the inverse pre-pass result at its permuted slot, runs the inverse FFT in registers and stores the windowed,
 // ifft-shifted frame with 8-byte stores.
 // ------------------------------------------------------------------------------------------------
-struct SynthBinLoader {
-    const DevPlan &p;
-    const float *__restrict__ gmag, *__restrict__ gph, *__restrict__ cmag, *__restrict__ cph;
-    const float *__restrict__ wphase;   // whisper phases of this (slice, channel)
-    int spec, kind;                     // DevRows::spec / DevRows::synth_kind
-
-    // analysis magnitude of bin i (FFT.cc:2624); with Cartesian spectra it is formed here, with the same operations
-    __device__ __forceinline__ float in_mag(int i) const {
-        if (!spec) return gmag[i];
-        const float r = gmag[i], q = gph[i];
-        return __fsqrt_rn(__fadd_rn(__fmul_rn(r, r), __fmul_rn(q, q)));
-    }
-    // (magnitude before the 1/N scale, phase) of packed bin i after the mode's spectral modification; for the constant
-    // mode on Cartesian spectra the pair is (re, im) and finish() only scales it
-    __device__ __forceinline__ float2 load(int i) const {
-        const int hs = p.half;
-        float m, ph;
-        if (cmag != nullptr) {  // modifySliceVocoder (:755-776)
-            m = cmag[i];
-            ph = cph[i];
-            const int band_len = p.N / 1024;
-            if (i == 0 || i == hs) {
-                m = 0.f;
-            } else if (band_len > 0) {
-                const int bs = (i / band_len) * band_len;
-                float mean = 0.f;
-                for (int e = 0; e < band_len; ++e) mean = __fadd_rn(mean, in_mag(bs + e));
-                m = __fmul_rn(m, __fdiv_rn(mean, (float)(band_len * 2)));
-            }
-        } else if (kind == 1) {         // roboticSlice (:805-812)
-            m = in_mag(i); ph = 0.f;
-        } else if (kind == 2) {         // whisperSlice (:814-822)
-            m = in_mag(i); ph = wphase[i];
-        } else if (kind == 3 && spec) { // constant mode: the spectrum goes back unchanged
-            m = gmag[i]; ph = gph[i];
-
-        } else if (p.freq_comp != 0.f) {  // freqCompSlice (:842-923) as a gather
-            if (p.freq_comp > 1.0f || i < hs) {
-                const int src = __float2int_rn(__fmul_rn((float)i, p.freq_comp));
-                if (src > hs) {
-                    m = 0.f; ph = 0.f;
-                } else {
-                    const float dw = (float)__ddiv_rn(__dmul_rn(p.two_pi_hop, (double)(i - src)), (double)p.N);
-                    m = gmag[src];
-                    ph = __fadd_rn(gph[src], dw);
-                }
-            } else {
-                m = gmag[i]; ph = gph[i];
-            }
-            m = __fmul_rn(m, p.fixed_gain);
-        } else {
-            m = gmag[i]; ph = gph[i];
-        }
-        return make_float2(m, ph);
-    }
-    // 1/N scale (:1024) and polar -> cartesian (FFT.cc:2711-2721)
-    __device__ __forceinline__ float2 finish(float2 mp) const {
-        const float m = __fmul_rn(mp.x, p.inv_n);
-        if (kind == 1 && cmag == nullptr) return make_float2(m, 0.f);                          // cosf(0) = 1, sinf(0) = 0
-        if (kind == 3 && spec && cmag == nullptr) return make_float2(m, __fmul_rn(mp.y, p.inv_n));   // (re, im) / N
-        float sn, cs;
-        sincosf(mp.y, &sn, &cs);
-        return make_float2(m * cs, m * sn);
-    }
-    __device__ __forceinline__ float2 operator()(int i) const { return finish(load(i)); }
-};
-
 // kLock: Cartesian spectra of the phase-locked core only (g.synth_kind == 4), no other mode's code; kWarp: + the formant /
 // gender frequency warp (p.warp_tab)
 template <int N, bool kLock, bool kWarp>
@@ -821,149 +740,9 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(
     const bool active = fid < total;
     const int row = active ? fid / nf : 0, f = active ? fid % nf : 0;
     const long k = k0 + f;
-    if (kLock && active) {
-        // Phase-locked core on Cartesian spectra: bin i of a locked frame is (re, im) * (cos, sin) of its region's rotation
-        // (pv_lock.cuh); first and classic frames, and the Nyquist bin, go back as they are.  1/N scale (:1024), then the
-        // inverse real-FFT pre-pass (kiss_fftr.c:123-159).  Four pairs per step: all their loads are issued before the
-        // dependent (cos, sin) gathers.
-        const int64_t slot = (int64_t)row * g.F + f;
-        const float *__restrict__ gre = g.mag + slot * p.Hp, *__restrict__ gim = g.phase + slot * p.Hp;
-        const bool locked = g.lock_hdr[slot].y == 2;
-        const unsigned short *__restrict__ lmap = g.lock_map + slot * p.half;
-        const float2 *__restrict__ lcsn = g.lock_csn + slot * g.maxpk;
-        const float2 *__restrict__ stw = p.stw_inv;
-        constexpr int Q = (NC / 2) / T;
-        constexpr int U = Q >= 4 ? 4 : Q;
-        const int sa = fft_pad(fft_slot_of_input<NC>(t)), sb = fft_pad(fft_slot_of_input<NC>((T - t) & (T - 1)));
-        const float inv_n = p.inv_n;
-        // formant / gender modes: freqCompSlice (:842-923) as a gather -- target bin i takes the locked bin src(i) turned by
-        // 2*pi*hop*(i - src)/N and scaled by the fixed gain; the host tabulates (gain cos, gain sin, src) per target bin
-        const float4 *__restrict__ wt = kWarp ? p.warp_tab : nullptr;
-#pragma unroll 1
-        for (int q0 = 0; q0 < Q; q0 += U) {
-            float2 lo[U], hi[U];
-            int sl[U], sh[U];
-            float2 wl[U], wh[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int kk = t + T * (q0 + u);
-                sl[u] = kk; sh[u] = NC - kk;
-                if (kWarp) {
-                    const float4 a4 = __ldg(&wt[kk]), b4 = __ldg(&wt[NC - kk]);
-                    sl[u] = __float_as_int(a4.z); sh[u] = __float_as_int(b4.z);
-                    wl[u] = make_float2(a4.x, a4.y); wh[u] = make_float2(b4.x, b4.y);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                lo[u] = make_float2(gre[sl[u]], gim[sl[u]]);
-                hi[u] = make_float2(gre[sh[u]], gim[sh[u]]);
-            }
-            if (locked) {
-                float2 cl[U], ch[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    cl[u] = lcsn[lmap[sl[u]]];
-                    ch[u] = sh[u] >= NC ? make_float2(1.f, 0.f) : lcsn[lmap[sh[u]]];   // bin NC (Nyquist) is not part of any region
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    lo[u] = make_float2(lo[u].x * cl[u].x - lo[u].y * cl[u].y, lo[u].x * cl[u].y + lo[u].y * cl[u].x);
-                    hi[u] = make_float2(hi[u].x * ch[u].x - hi[u].y * ch[u].y, hi[u].x * ch[u].y + hi[u].y * ch[u].x);
-                }
-            }
-            if (kWarp) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    lo[u] = make_float2(lo[u].x * wl[u].x - lo[u].y * wl[u].y, lo[u].x * wl[u].y + lo[u].y * wl[u].x);
-                    hi[u] = make_float2(hi[u].x * wh[u].x - hi[u].y * wh[u].y, hi[u].x * wh[u].y + hi[u].y * wh[u].x);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int q = q0 + u, kk = t + T * q;
-                const float2 fk = make_float2(__fmul_rn(lo[u].x, inv_n), __fmul_rn(lo[u].y, inv_n));
-                const float2 fq = make_float2(__fmul_rn(hi[u].x, inv_n), __fmul_rn(hi[u].y, inv_n));
-                if (kk == 0) {
-                    buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk.x + fq.x, fk.x - fq.x);
-                } else {
-                    const float2 fnkc = make_float2(fq.x, -fq.y);
-                    const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
-                    const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
-                    const float2 a = cadd_rn(fek, fok);
-                    const float2 b = csub_rn(fek, fok);
-                    buf[sa + fft_pad(fft_slot_of_input<NC>(T * q))] = a;
-                    buf[sb + (t == 0 ? fft_pad(fft_slot_of_input<NC>((T * (16 - q)) & (NC - 1))) : fft_pad(fft_slot_of_input<NC>(T * (15 - q))))] =
-                        make_float2(b.x, -b.y);
-                }
-            }
-        }
-        if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)
-            int src = NC / 2;
-            float2 w = make_float2(1.f, 0.f);
-            if (kWarp) { const float4 a4 = __ldg(&wt[NC / 2]); src = __float_as_int(a4.z); w = make_float2(a4.x, a4.y); }
-            float2 fk = make_float2(gre[src], gim[src]);
-            if (locked && src < NC) {
-                const float2 cs = lcsn[lmap[src]];
-                fk = make_float2(fk.x * cs.x - fk.y * cs.y, fk.x * cs.y + fk.y * cs.x);
-            }
-            if (kWarp) fk = make_float2(fk.x * w.x - fk.y * w.y, fk.x * w.y + fk.y * w.x);
-            fk = make_float2(__fmul_rn(fk.x, inv_n), __fmul_rn(fk.y, inv_n));
-            const float2 fnkc = make_float2(fk.x, -fk.y);
-            const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
-            const float2 fok = cmul_rn(d, __ldg(&stw[NC / 2]));
-            const float2 b = csub_rn(fek, fok);
-            buf[fft_pad(fft_slot_of_input<NC>(NC / 2))] = make_float2(b.x, -b.y);
-        }
-    }
-    if (!kLock && active) {
-        const int64_t so = ((int64_t)row * g.F + f) * p.Hp;
-        const int64_t co = (int64_t)(k - g.aux_base) * p.Hp;
-        const float *wph = g.whisper ? g.whisper + ((int64_t)(k - g.aux_base) * g.channels + row % g.channels) * p.H : nullptr;
-        const SynthBinLoader bin{p, g.mag + so, g.phase + so, car_mag ? car_mag + co : nullptr, car_mag ? car_phase + co : nullptr, wph, g.spec, g.synth_kind};
-        const float2 *__restrict__ stw = p.stw_inv;
-        // inverse real-FFT pre-pass (kiss_fftr.c:123-159).  All loads of the thread's bins are issued before any of the
-        // (long) sincos evaluations so their latency overlaps.
-        constexpr int Q = (NC / 2) / T;
-        const int sa = fft_pad(fft_slot_of_input<NC>(t)), sb = fft_pad(fft_slot_of_input<NC>((T - t) & (T - 1)));
-        // rolled in groups of two pairs: four independent loads in flight per step without unrolling the (large) sincos
-        // expansion 16 times, which would not fit the instruction cache
-#pragma unroll 1
-        for (int q0 = 0; q0 < Q; q0 += 2) {
-            float2 lo[2], hi[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                lo[u] = bin.load(t + T * (q0 + u));
-                hi[u] = bin.load(NC - (t + T * (q0 + u)));
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int q = q0 + u, kk = t + T * q;
-                const float2 fk = bin.finish(lo[u]);
-                const float2 fq = bin.finish(hi[u]);
-                if (kk == 0) {
-                    buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk.x + fq.x, fk.x - fq.x);
-                } else {
-                    const float2 fnkc = make_float2(fq.x, -fq.y);
-                    const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
-                    const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
-                    const float2 a = cadd_rn(fek, fok);
-                    const float2 b = csub_rn(fek, fok);
-                    // slot(t + T*q) = slot(t) | slot(T*q) and the padded position is additive (see k_analyse_t)
-                    buf[sa + fft_pad(fft_slot_of_input<NC>(T * q))] = a;
-                    buf[sb + (t == 0 ? fft_pad(fft_slot_of_input<NC>((T * (16 - q)) & (NC - 1))) : fft_pad(fft_slot_of_input<NC>(T * (15 - q))))] =
-                        make_float2(b.x, -b.y);
-                }
-            }
-        }
-        if (t == 0) {   // kk == NC/2 pairs with itself; the reference's second write wins (kiss_fftr.c:150-155)
-            const float2 fk = bin(NC / 2);
-            const float2 fnkc = make_float2(fk.x, -fk.y);
-            const float2 fek = cadd_rn(fk, fnkc), d = csub_rn(fk, fnkc);
-            const float2 fok = cmul_rn(d, __ldg(&stw[NC / 2]));
-            const float2 b = csub_rn(fek, fok);
-            buf[fft_pad(fft_slot_of_input<NC>(NC / 2))] = make_float2(b.x, -b.y);
-        }
+    if (active) {   // inverse real-FFT pre-pass into the frame's exchange buffer (pv_synth.cuh)
+        if (kLock) synth_prepass_lock<N, kWarp>(p, g, row, f, t, buf);
+        else synth_prepass_generic<N>(p, g, car_mag, car_phase, row, f, k, t, buf);
     }
     frame_sync<T>(group);
     float2 v[16];
@@ -1130,89 +909,11 @@ __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const 
     // works on one phase: the sinc quad of every tap is a single broadcast shared-memory access, and the lanes' input
     // windows are a constant few samples apart (bank-conflict free).
     const ResampleRun &hdr = s_hdr;   // fetched into shared memory at the start of the kernel
-    constexpr int nb = OV > 0 ? OV : 1;
-    const unsigned *__restrict__ ent_tab = rs_ent + hdr.ent_off;
-    const float *__restrict__ frac_tab = rs_frac + hdr.ent_off;
     const int64_t orow = row_out + hdr.out_first;
     const int64_t out_limit = g.n_out[row] - hdr.out_first;
     const int in_shift = (int)(hdr.u_lo - u_lo) - kResPad;   // hdr.u_lo == u_lo; entries are biased by kResPad
     (void)out_first;
-    // kResBlock entries (one phase) per warp step, kResPerThread outputs per thread: the quad of a tap is loaded once and
-    // feeds 4 x kResPerThread FMAs (a 128-bit shared load costs four wavefronts even when it is a broadcast)
-    const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
-    for (int blk = warp * kResBlock; blk < hdr.padded; blk += nwarp * kResBlock) {
-        int bucket = 0;
-#pragma unroll
-        for (int q = 1; q < nb; ++q) bucket += hdr.start[q] <= blk;   // warp-uniform
-        unsigned ent[kResPerThread];
-        const float *xs[kResPerThread];
-        bool live[kResPerThread];
-#pragma unroll
-        for (int u = 0; u < kResPerThread; ++u) {
-            ent[u] = __ldg(&ent_tab[blk + lane + 32 * u]);
-            live[u] = ent[u] != 0xffffffffu && (int64_t)(ent[u] & 0xffffu) < out_limit;
-            // tap 0; may reach into the zero history before s_in[0]; dead entries read (and discard) from a safe place
-            xs[u] = live[u] ? s_in + ((int)(ent[u] >> 16) + in_shift) : s_in;
-        }
-        if (OV == 0) {
-#pragma unroll
-            for (int u = 0; u < kResPerThread; ++u) {
-                if (!live[u]) continue;
-                float sum = 0.f;
-                const float *__restrict__ tt = p.rs_table + (size_t)__float_as_uint(__ldg(&frac_tab[blk + lane + 32 * u])) * L;
-                for (int j = 0; j < L; ++j) sum += xs[u][j] * __ldg(&tt[j]);
-                pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), sum);
-            }
-        } else {
-            const int qoff = 4 + OV - bucket;
-            auto quad_at = [&](int tap) -> float4 { return s_quad[qoff + tap * OV]; };   // warp-uniform: a broadcast load
-            float acc[kResPerThread][4];
-#pragma unroll
-            for (int u = 0; u < kResPerThread; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
-            // two taps per stage, two stages in flight: the loads of the next stage are issued before the 32 FMAs of the
-            // current one (filt_len is a multiple of 4, resample.c:712)
-            float4 tqa[2], tqb[2];
-            float xa[2][kResPerThread], xb[2][kResPerThread];
-            auto load2 = [&](int j, float4 (&tq)[2], float (&x)[2][kResPerThread]) {
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    tq[jj] = quad_at(j + jj);
-#pragma unroll
-                    for (int u = 0; u < kResPerThread; ++u) x[jj][u] = xs[u][j + jj];
-                }
-            };
-            auto fma2 = [&](const float4 (&tq)[2], const float (&x)[2][kResPerThread]) {
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                    for (int u = 0; u < kResPerThread; ++u) {
-                        acc[u][0] += x[jj][u] * tq[jj].x;
-                        acc[u][1] += x[jj][u] * tq[jj].y;
-                        acc[u][2] += x[jj][u] * tq[jj].z;
-                        acc[u][3] += x[jj][u] * tq[jj].w;
-                    }
-            };
-            load2(0, tqa, xa);
-#pragma unroll 1
-            for (int j = 0; j < L; j += 4) {
-                load2(j + 2, tqb, xb);
-                fma2(tqa, xa);
-                if (j + 4 < L) load2(j + 4, tqa, xa);
-                fma2(tqb, xb);
-            }
-#pragma unroll
-            for (int u = 0; u < kResPerThread; ++u) {
-                if (!live[u]) continue;
-                const float frac = __ldg(&frac_tab[blk + lane + 32 * u]);
-                // cubic_coef (resample.c:339-351)
-                const float i0 = -0.16667f * frac + 0.16667f * frac * frac * frac;
-                const float i1 = frac + 0.5f * frac * frac - 0.5f * frac * frac * frac;
-                const float i3 = -0.33333f * frac + 0.5f * frac * frac - 0.16667f * frac * frac * frac;
-                const float i2 = (float)(1. - i0 - i1 - i3);
-                pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), (i0 * acc[u][0]) + (i1 * acc[u][1]) + (i2 * acc[u][2]) + (i3 * acc[u][3]));
-            }
-        }
-    }
+    resample_run<OV>(p, g, hdr, s_quad, s_in, in_shift, orow, out_limit, rs_ent, rs_frac, L);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -62,6 +62,9 @@ struct DevRows {
     float *lock_tail;         // [rows][2][Hp]: (re, im) of the last frame of the previous launch
     int *lock_kind;           // [rows]: chain state of the channel (kind 0..3, see pv_lock.cuh)
     float *lock_rot;          // [rows][maxpk]: rotations of the channel's previous frame (kind 2); kind 1 keeps prev_out
+    // fused inverse FFT + overlap-add + resampler (pv_fused.cu): what a row carries from one launch to the next
+    float *ola_tail;          // [rows][N]: the unfinished part of the overlap-add accumulator (from the next slice's position on)
+    float *res_hist;          // [rows][filt_len + 8]: the last normalised samples (resampler history), zeros before the stream
     long aux_base;            // slice index of element 0 of the whisper table / carrier spectra
     int spec;                 // 0: spectra are (mag, phase); 1: Cartesian (re in mag[], im in phase[]) -- modes that never use the
                               //    analysis phase (robotic, whisper, vocoder, constant) and the phase-locked core of the plain
@@ -106,6 +109,23 @@ int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out);
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
                          long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
                          long run_origin, cudaStream_t st);
+// Fused inverse FFT + window + overlap-add + normalisation + resampler (k_synth_ola, pv_fused.cu): one CTA per row runs the
+// frames [k0, k0 + nf) of a chunk in order, `run` frames per round (a multiple of the frames it has in flight).
+struct FusedArgs {
+    const SliceRec *recs; long recs_base;
+    const float *norm; int64_t norm_base;
+    long k0; int nf;
+    int run;          // frames per round = slices per resampler work list
+    int acc_len;      // floats of the shared-memory accumulator ring: power of two >= N + (run - 1) * largest shift increment
+    int in_len;       // floats of the resampler input window: hist_len + run * largest per-slice contribution (+ pad)
+    int hist_len;     // filt_len + 8 normalised samples carried between rounds / launches (0 without resampler)
+    const ResampleRun *runs; const unsigned *rs_ent; const float *rs_frac; long run_origin;
+    const float *car_mag, *car_phase;   // vocoder carrier spectra or null
+};
+int fused_frames_in_flight(int N);   // 0: this FFT size has no fused kernel
+bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_consumed, int max_out, size_t smem_limit, FusedArgs *out);
+cudaError_t launch_synth_ola(const DevPlan &p, const DevRows &g, const FusedArgs &a, cudaStream_t st);
+
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
 

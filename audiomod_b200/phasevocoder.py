@@ -180,7 +180,11 @@ class PhaseVocoderBatch:
         self.run_host_rows(in_rows, out_rows, fmt)
         return outs
 
-    KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "ola_resample", "unused", "fixed_phase", "lock_peaks", "lock_chain")
+    def set_fused(self, enable: bool = True):
+        """Fused inverse-FFT + overlap-add + resampler kernel (default) or the split kernels; bit-identical results."""
+        check(_lib.lib().pvgpu_batch_set_fused(self._h, int(bool(enable))))
+
+    KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "ola_resample", "synth_ola", "fixed_phase", "lock_peaks", "lock_chain")
 
     def profile(self, enable=True):
         check(_lib.lib().pvgpu_batch_profile(self._h, int(bool(enable))))
@@ -292,3 +296,23 @@ class HostBuffer:
             self.ptr = C.c_void_p()
 
     __del__ = close
+
+
+def run_wav_files(pairs, timeratio=1.0, pitchshift=0.0, mode=NORMAL_SHIFT, coremode=PHASE_LOCKED, fftsize=2048, hopsize=0, devices=None):
+    """File -> file batch: every (in.wav, out.wav) pair is processed like `audiomod-exe <effect> in.wav out.wav ...`
+    (pvgpu_run_wav_files).  Returns one dict per file (status, message, sample_rate, channels, bits, frames_in, frames_out)."""
+    n = len(pairs)
+    jobs = (_lib.WavJob * max(n, 1))()
+    keep = []
+    for i, (a, b) in enumerate(pairs):
+        keep.append((str(a).encode(), str(b).encode()))
+        jobs[i].in_path, jobs[i].out_path = keep[-1]
+    devs = list(devices) if devices is not None else []
+    arr = (C.c_int * max(len(devs), 1))(*devs)
+    rc = _lib.lib().pvgpu_run_wav_files(C.byref(_cfg(0, 0, timeratio, pitchshift, mode, coremode, fftsize, hopsize, 0)), jobs, n,
+                                        arr if devs else None, len(devs))
+    out = [dict(status=jobs[i].status, message=jobs[i].message.decode(errors="replace"), sample_rate=jobs[i].sample_rate,
+                channels=jobs[i].channels, bits=jobs[i].bits, frames_in=jobs[i].frames_in, frames_out=jobs[i].frames_out) for i in range(n)]
+    if rc != _lib.OK and all(j["status"] == _lib.OK for j in out):
+        check(rc)
+    return out

@@ -116,7 +116,7 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
 int pvgpu_batch_stats(const pvgpu_batch *b, int64_t *kernel_launches, int64_t *slices, int64_t *h2d_bytes, int64_t *d2h_bytes);
 int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);
 /* Per-kernel device timing with CUDA events recorded on the launching stream around every launch.  kinds:
- * 0 analyse, 1 phase core (polar), 2 synthesise, 3 overlap-add + resample, 5 fixed phase (robotic/whisper on polar spectra),
+ * 0 analyse, 1 phase core (polar), 2 synthesise, 3 overlap-add + resample, 4 fused synthesise + overlap-add + resample, 5 fixed phase (robotic/whisper on polar spectra),
  * 6 lock_peaks, 7 lock_chain (phase-locked core on Cartesian spectra).
  * pvgpu_batch_kernel_times synchronises the device and returns the totals since profiling was enabled. */
 enum { PVGPU_KINDS = 8 };
@@ -126,6 +126,11 @@ int pvgpu_batch_kernel_times(pvgpu_batch *b, double *ms /*[PVGPU_KINDS]*/, int64
  * and equal-length batches in evenly spaced host rows are pipelined along time; an explicit value selects pipelining
  * across row groups); how many row groups are in flight at once (1..4; each has its own stream, workspace and staging) */
 int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, int contexts);
+/* Resynthesis back end: 1 (default) = the fused inverse-FFT + overlap-add + resampler kernel with the accumulator in shared
+ * memory wherever the FFT size has one (512..8192); 0 = the split kernels (inverse FFT -> frame ring in HBM -> overlap-add +
+ * resampler).  Both produce bit-identical samples (tests/test_gpu_fused.py); the switch exists for A/B measurements.  The
+ * environment variable PVGPU_FUSED=0 does the same for every instance, including streaming ones. */
+int pvgpu_batch_set_fused(pvgpu_batch *b, int enable);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU batch: the same streams sharded across several devices of one box (BASELINE.json configs[3]: "4096 streams
@@ -158,6 +163,22 @@ int pvgpu_host_info(const void *ptr, int *numa_node, int *hugepages, size_t *byt
 /* NUMA node of a CUDA device from sysfs (-1 when unknown); pin the calling thread to that node's cores */
 int pvgpu_device_numa_node(int device);
 int pvgpu_bind_thread_to_device(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * File -> file: what `audiomod-exe <effect> in.wav out.wav <args>` does for one file (main/main.cc:95-161, 471-509 and the
+ * RIFF reader / writer main/wavfile.cc:672-812, 848-1016, 1135-1182, 1294-1306, 1474-1526), for many files in one call.
+ * Input: RIFF/WAVE integer PCM, 8/16/24/32 bit, mono or stereo; output: 16-bit PCM with the reference's 56-byte header
+ * (main.cc:136).  cfg->sample_rate and cfg->channels are ignored (taken from each file; files are grouped into one batch per
+ * (sample rate, channels, 16-bit or not)); devices as in pvgpu_mbatch_create.  Per-file results are reported in the jobs.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct pvgpu_wav_job {
+    const char *in_path, *out_path;
+    int status;                         /* out: PVGPU_OK or this file's error code */
+    int sample_rate, channels, bits;    /* out: from the input header */
+    int64_t frames_in, frames_out;      /* out: samples per channel read / written */
+    char message[160];                  /* out: error text */
+} pvgpu_wav_job;
+int pvgpu_run_wav_files(const pvgpu_config *cfg, pvgpu_wav_job *jobs, int n_jobs, const int *devices, int n_dev);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage hooks for the parity tests (tests/ compares each stage with the CPU oracle).  Device work,
