@@ -63,6 +63,32 @@ struct DevBuf {
     template <typename T> T *as() const { return (T *)p; }
 };
 
+// Page-locked staging area of a streaming instance: everything one pvgpu_process call uploads (new input, slice records,
+// normalisers, resampler work lists) is copied here first so that the H2D copies are truly asynchronous and the call needs a
+// single synchronisation, and the call's output comes back through it.  Bump allocation, reset once per call.
+struct PinnedArena {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    ~PinnedArena() { if (base) cudaFreeHost(base); }
+    // only between calls (nothing in flight): make room for at least `bytes`
+    void reserve(size_t bytes) {
+        used = 0;
+        if (bytes <= cap) return;
+        if (base) cudaFreeHost(base);
+        base = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 2 + 4096;
+        if (cudaHostAlloc((void **)&base, want, cudaHostAllocDefault) == cudaSuccess) cap = want;
+        else { cudaGetLastError(); base = nullptr; }
+    }
+    void *take(size_t bytes) {
+        bytes = (bytes + 63) & ~(size_t)63;
+        if (!base || used + bytes > cap) return nullptr;
+        void *p = base + used;
+        used += bytes;
+        return p;
+    }
+};
+
 static Config to_config(const pvgpu_config &c) {
     Config k;
     k.sample_rate = c.sample_rate; k.channels = c.channels; k.time_ratio = c.time_ratio; k.pitch_semitones = c.pitch_semitones;
@@ -109,7 +135,7 @@ struct Pipeline {
     FusedArgs fa{};             // run / ring / window shape; per-launch fields are filled in run_synth_ola
     // host copy of the uploaded records + the resampler work lists built from them (ResampleRun, pv_kernels.cuh)
     std::vector<SliceRec> h_recs;
-    DevBuf b_runs, b_rsent, b_rsfrac;
+    DevBuf b_runs, b_rsent, b_rsfrac, b_rssteps;
     long run_origin = 0;
     int table_run = 1;
     int64_t launches = 0;
@@ -262,6 +288,24 @@ struct Pipeline {
         return PVGPU_OK;
     }
 
+    // H2D on `st`: through the instance's pinned arena when there is one (asynchronous, the source may be a temporary),
+    // else straight from the caller's memory -- then the caller must synchronise before the source goes away (staged_all)
+    PinnedArena *arena = nullptr;
+    bool staged_all = true;
+    int h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+        if (!bytes) return PVGPU_OK;
+        void *pin = arena ? arena->take(bytes) : nullptr;
+        if (pin) { std::memcpy(pin, src, bytes); src = pin; } else staged_all = false;
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return PVGPU_OK;
+    }
+    // work-list scratch of build_resample_runs (members so that a streaming instance does not allocate per call)
+    struct RunScratch {
+        std::vector<ResampleRun> runs;
+        std::vector<unsigned> ent, steps, run_steps, be[kMaxBuckets], e2;
+        std::vector<float> frac, bf[kMaxBuckets], f2;
+    } rsx;
+
     static int upload(DevBuf &b, const void *src, size_t bytes) {
         CU(b.ensure(bytes ? bytes : 4));
         if (bytes) CU(cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice));
@@ -294,8 +338,9 @@ struct Pipeline {
         const auto &norm = s.norm();
         CU(b_recs.ensure(sizeof(SliceRec) * std::max<size_t>(recs.size(), 1)));
         CU(b_norm.ensure(sizeof(float) * std::max<size_t>(norm.size(), 1)));
-        if (!recs.empty()) CU(cudaMemcpyAsync(b_recs.p, recs.data(), sizeof(SliceRec) * recs.size(), cudaMemcpyHostToDevice, st));
-        if (!norm.empty()) CU(cudaMemcpyAsync(b_norm.p, norm.data(), sizeof(float) * norm.size(), cudaMemcpyHostToDevice, st));
+        int rc;
+        if ((rc = h2d(b_recs.p, recs.data(), sizeof(SliceRec) * recs.size(), st))) return rc;
+        if ((rc = h2d(b_norm.p, norm.data(), sizeof(float) * norm.size(), st))) return rc;
         recs_base = s.recs_base();
         recs_count = (long)recs.size();
         norm_base = s.norm_base();
@@ -312,11 +357,12 @@ struct Pipeline {
         if (!p.rs_active) return PVGPU_OK;
         const int L = (int)p.rs_filt_len, ov = (int)p.rs_oversample, nb = p.rs_direct ? 1 : ov;
         if (L > kResPad) return fail(PVGPU_EINVAL, "resampler filter of %d taps is not supported (max %d)", L, kResPad);
-        std::vector<ResampleRun> runs;
-        std::vector<unsigned> ent;
-        std::vector<float> frac;
-        std::vector<unsigned> be[kMaxBuckets];
-        std::vector<float> bf[kMaxBuckets];
+        std::vector<ResampleRun> &runs = rsx.runs;
+        std::vector<unsigned> &ent = rsx.ent, &steps = rsx.steps, &run_steps = rsx.run_steps;
+        std::vector<float> &frac = rsx.frac;
+        std::vector<unsigned> (&be)[kMaxBuckets] = rsx.be;
+        std::vector<float> (&bf)[kMaxBuckets] = rsx.bf;
+        runs.clear(); ent.clear(); frac.clear(); steps.clear(); run_steps.clear();
         for (long ka = origin; ka < end; ka += run) {
             const long kb = std::min<long>(ka + run, end);
             const SliceRec &ra = h_recs[ka - recs_base];
@@ -358,44 +404,60 @@ struct Pipeline {
                     constexpr int kWin = 2 * kResBlock;   // entries permuted together: wider = fewer conflicts, but more scattered stores
                     for (size_t b0 = 0; b0 < e.size(); b0 += kWin) {
                         const int n = (int)std::min<size_t>(kWin, e.size() - b0), nrow = (n + 31) / 32;
-                        std::vector<std::vector<int>> rows(nrow);
-                        std::vector<int> spill;
+                        int rows[kWin / 32][32], cnt[kWin / 32] = {}, spill[kWin], nspill = 0;
                         int seen[32] = {};   // the r-th entry of a bank goes to row r
                         for (int i = 0; i < n; ++i) {
                             const int r = seen[(e[b0 + i] >> 16) & 31u]++;
-                            if (r < nrow && rows[r].size() < 32) rows[r].push_back(i); else spill.push_back(i);
+                            if (r < nrow && cnt[r] < 32) rows[r][cnt[r]++] = i; else spill[nspill++] = i;
                         }
-                        size_t sp = 0;   // entries without a conflict-free row fill the rows that are not full, last row last
+                        int sp = 0;   // entries without a conflict-free row fill the rows that are not full, last row last
                         for (int r = 0; r < nrow; ++r) {
-                            const size_t want = r + 1 < nrow ? 32 : (size_t)(n - 32 * (nrow - 1));
-                            while (rows[r].size() < want && sp < spill.size()) rows[r].push_back(spill[sp++]);
-                            for (int r2 = nrow - 1; r2 > r && rows[r].size() < want; --r2)
-                                while (rows[r].size() < want && !rows[r2].empty()) { rows[r].push_back(rows[r2].back()); rows[r2].pop_back(); }
+                            const int want = r + 1 < nrow ? 32 : n - 32 * (nrow - 1);
+                            while (cnt[r] < want && sp < nspill) rows[r][cnt[r]++] = spill[sp++];
+                            for (int r2 = nrow - 1; r2 > r && cnt[r] < want; --r2)
+                                while (cnt[r] < want && cnt[r2] > 0) rows[r][cnt[r]++] = rows[r2][--cnt[r2]];
                         }
-                        std::vector<unsigned> e2;
-                        std::vector<float> f2;
-                        for (int r = 0; r < nrow; ++r) for (int i : rows[r]) { e2.push_back(e[b0 + i]); f2.push_back(f[b0 + i]); }
-                        for (size_t i = sp; i < spill.size(); ++i) { e2.push_back(e[b0 + spill[i]]); f2.push_back(f[b0 + spill[i]]); }
+                        std::vector<unsigned> &e2 = rsx.e2;
+                        std::vector<float> &f2 = rsx.f2;
+                        e2.clear(); f2.clear();
+                        for (int r = 0; r < nrow; ++r) for (int c = 0; c < cnt[r]; ++c) { e2.push_back(e[b0 + rows[r][c]]); f2.push_back(f[b0 + rows[r][c]]); }
+                        for (int i = sp; i < nspill; ++i) { e2.push_back(e[b0 + spill[i]]); f2.push_back(f[b0 + spill[i]]); }
                         std::copy(e2.begin(), e2.end(), e.begin() + b0);
                         std::copy(f2.begin(), f2.end(), f.begin() + b0);
                     }
                 }
                 ent.insert(ent.end(), be[q].begin(), be[q].end());
                 frac.insert(frac.end(), bf[q].begin(), bf[q].end());
+                const int first = pos;
                 pos += (int)be[q].size();
-                while (pos % kResBlock) { ent.push_back(0xffffffffu); frac.push_back(0.f); ++pos; }
+                while (pos % 32) { ent.push_back(0xffffffffu); frac.push_back(0.f); ++pos; }   // whole rows of 32 lanes
+                // warp steps of this phase: up to kResPerThread rows each, a short one last
+                for (int r0 = first / 32; r0 < pos / 32; r0 += kResPerThread) {
+                    const int rows = std::min(kResPerThread, pos / 32 - r0);
+                    if ((unsigned)(r0 * 32) > 0xfffffu) return fail(PVGPU_ESTATE, "resampler run does not fit its step list");
+                    run_steps.push_back((unsigned)(r0 * 32) | ((unsigned)(rows - 1) << 20) | ((unsigned)q << 24));
+                }
             }
             for (int q = nb; q <= kMaxBuckets; ++q) hdr.start[q] = pos;
             hdr.padded = pos;
+            // long steps first: the CTA's warps take the steps round-robin
+            std::stable_sort(run_steps.begin(), run_steps.end(), [](unsigned a, unsigned b) { return ((a >> 20) & 7u) > ((b >> 20) & 7u); });
+            hdr.step_off = (int)steps.size();
+            hdr.n_steps = (int)run_steps.size();
+            steps.insert(steps.end(), run_steps.begin(), run_steps.end());
+            run_steps.clear();
             runs.push_back(hdr);
         }
         CU(b_runs.ensure(sizeof(ResampleRun) * std::max<size_t>(runs.size(), 1)));
         CU(b_rsent.ensure(sizeof(unsigned) * std::max<size_t>(ent.size(), 1)));
         CU(b_rsfrac.ensure(sizeof(float) * std::max<size_t>(frac.size(), 1)));
-        if (!runs.empty()) CU(cudaMemcpyAsync(b_runs.p, runs.data(), sizeof(ResampleRun) * runs.size(), cudaMemcpyHostToDevice, st));
-        if (!ent.empty()) CU(cudaMemcpyAsync(b_rsent.p, ent.data(), sizeof(unsigned) * ent.size(), cudaMemcpyHostToDevice, st));
-        if (!frac.empty()) CU(cudaMemcpyAsync(b_rsfrac.p, frac.data(), sizeof(float) * frac.size(), cudaMemcpyHostToDevice, st));
-        CU(cudaStreamSynchronize(st));   // the host vectors are temporaries
+        CU(b_rssteps.ensure(sizeof(unsigned) * std::max<size_t>(steps.size(), 1)));
+        int rc;
+        if ((rc = h2d(b_runs.p, runs.data(), sizeof(ResampleRun) * runs.size(), st))) return rc;
+        if ((rc = h2d(b_rsent.p, ent.data(), sizeof(unsigned) * ent.size(), st))) return rc;
+        if ((rc = h2d(b_rsfrac.p, frac.data(), sizeof(float) * frac.size(), st))) return rc;
+        if ((rc = h2d(b_rssteps.p, steps.data(), sizeof(unsigned) * steps.size(), st))) return rc;
+        if (!staged_all) { CU(cudaStreamSynchronize(st)); staged_all = true; }   // sources that were not staged are reused by the next call
         return PVGPU_OK;
     }
 
@@ -451,7 +513,8 @@ struct Pipeline {
         if (!allow_fused || (env && env[0] == '0')) return false;
         if (fused_frames_in_flight(p.N) == 0) return false;
         FusedArgs a{};
-        if (!fused_plan(p, frames_per_chunk, max_shift, max_shift, max_out_bound, (size_t)200 * 1024, &a)) return false;
+        const char *fr = std::getenv("PVGPU_FUSED_RUN");
+        if (!fused_plan(p, frames_per_chunk, max_shift, max_shift, max_out_bound, (size_t)200 * 1024, fr ? std::atoi(fr) : 0, &a)) return false;
         fa = a;
         fused = true;
         return true;
@@ -461,7 +524,7 @@ struct Pipeline {
         a.recs = b_recs.as<SliceRec>(); a.recs_base = recs_base;
         a.norm = b_norm.as<float>(); a.norm_base = norm_base;
         a.k0 = k0; a.nf = nf;
-        a.runs = b_runs.as<ResampleRun>(); a.rs_ent = b_rsent.as<unsigned>(); a.rs_frac = b_rsfrac.as<float>(); a.run_origin = run_origin;
+        a.runs = b_runs.as<ResampleRun>(); a.rs_ent = b_rsent.as<unsigned>(); a.rs_frac = b_rsfrac.as<float>(); a.rs_steps = b_rssteps.as<unsigned>(); a.run_origin = run_origin;
         a.car_mag = d.vocoder ? b_carmag.as<float>() : nullptr; a.car_phase = d.vocoder ? b_carph.as<float>() : nullptr;
         Span *sp = span_begin(4, st);
         CU(launch_synth_ola(p, g, a, st));
@@ -472,7 +535,7 @@ struct Pipeline {
         const SliceRec *recs = b_recs.as<SliceRec>();
         Span *sp = span_begin(3, st);
         launch_ola_resample(p, g, recs, b_norm.as<float>(), norm_base, recs_base, k0, nf, table_run, max_consumed, b_runs.as<ResampleRun>(),
-                            b_rsent.as<unsigned>(), b_rsfrac.as<float>(), run_origin, st);
+                            b_rsent.as<unsigned>(), b_rsfrac.as<float>(), b_rssteps.as<unsigned>(), run_origin, st);
         span_end(sp, st); ++launches;
     }
     int run_frames(const DevRows &g, long k0, int nf, cudaStream_t st) {
@@ -1247,12 +1310,15 @@ struct pvgpu_stream {
     size_t fifo_rd = 0;
     int num_res = 0;
     DevBuf d_in, d_out, d_car, d_len;
-    std::vector<float> h_stage;
+    std::vector<float> h_stage, scratch;
+    PinnedArena arena;
     cudaStream_t st = nullptr;
     static constexpr int kF = 64;
     ~pvgpu_stream() { if (st) cudaStreamDestroy(st); }
 };
 
+// One pvgpu_process call that completed `added` new slices starting at slice k0.  Steady state: no heap allocation (the
+// vectors keep their capacity), every upload goes through the page-locked arena, one stream synchronisation at the end.
 static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     Pipeline &pl = s->pl;
     Scheduler &sc = *s->sched;
@@ -1261,22 +1327,30 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     CU(cudaSetDevice(pl.device));
     const int64_t len = (int64_t)s->tail[0].size();
     const int64_t in_stride = std::max<int64_t>((len + 3) & ~(int64_t)3, 4);
-    CU(s->d_in.ensure(sizeof(float) * (size_t)C * in_stride));
-    for (int c = 0; c < C; ++c)
-        if (len) CU(cudaMemcpyAsync(s->d_in.as<float>() + c * in_stride, s->tail[c].data(), sizeof(float) * len, cudaMemcpyHostToDevice, s->st));
-    // per-row limits: [0..C) valid input end, [C..2C) output limit, [2C] carrier length
-    std::vector<int64_t> lim(2 * C + 1);
-    for (int c = 0; c < C; ++c) { lim[c] = s->in_base + len; lim[C + c] = INT64_MAX; }
-    lim[2 * C] = s->in_base + (int64_t)s->car_tail.size();
-    CU(s->d_len.ensure(sizeof(int64_t) * lim.size()));
-    CU(cudaMemcpyAsync(s->d_len.p, lim.data(), sizeof(int64_t) * lim.size(), cudaMemcpyHostToDevice, s->st));
-    int rc;
-    if ((rc = pl.upload_schedule(sc, s->st))) return rc;
-    if ((rc = pl.build_resample_runs(k0, k0 + added, pl.fused ? pl.fa.run : ola_run_limit(p, 8, pl.max_consumed, pl.max_out), s->st))) return rc;
     const SliceRec &first = sc.recs()[k0 - sc.recs_base()];
     const int64_t out_base = first.out_off;
     const int64_t new_out = sc.total_out() - out_base;
     const int64_t out_stride = std::max<int64_t>((new_out + 3) & ~(int64_t)3, 4);
+    {   // room for everything this call stages (nothing is in flight between calls)
+        const size_t lists = p.rs_active ? (size_t)(new_out + 8 * 32 * ((added + 3) / 4 + 1) + 64) * 12 + (size_t)added * sizeof(ResampleRun) : 0;
+        const size_t need = sizeof(float) * ((size_t)C * len + s->car_tail.size() + sc.norm().size() + (size_t)C * new_out) + sizeof(SliceRec) * sc.recs().size() +
+                            lists + (pl.d.whisper ? sizeof(float) * (size_t)added * C * p.H : 0) + 64 * 16 + sizeof(int64_t) * (2 * C + 1);
+        s->arena.reserve(need);
+        pl.arena = &s->arena;
+        pl.staged_all = true;
+    }
+    int rc;
+    CU(s->d_in.ensure(sizeof(float) * (size_t)C * in_stride));
+    for (int c = 0; c < C; ++c)
+        if ((rc = pl.h2d(s->d_in.as<float>() + c * in_stride, s->tail[c].data(), sizeof(float) * len, s->st))) return rc;
+    // per-row limits: [0..C) valid input end, [C..2C) output limit, [2C] carrier length
+    int64_t lim[2 * 16 + 1];
+    for (int c = 0; c < C; ++c) { lim[c] = s->in_base + len; lim[C + c] = INT64_MAX; }
+    lim[2 * C] = s->in_base + (int64_t)s->car_tail.size();
+    CU(s->d_len.ensure(sizeof(int64_t) * (2 * 16 + 1)));
+    if ((rc = pl.h2d(s->d_len.p, lim, sizeof(int64_t) * (2 * C + 1), s->st))) return rc;
+    if ((rc = pl.upload_schedule(sc, s->st))) return rc;
+    if ((rc = pl.build_resample_runs(k0, k0 + added, pl.fused ? pl.fa.run : ola_run_limit(p, 8, pl.max_consumed, pl.max_out), s->st))) return rc;
     CU(s->d_out.ensure(sizeof(float) * (size_t)C * out_stride));
     if (!pl.fused && halo_of(sc.recs(), sc.recs_base(), p.rs_active ? (int)p.rs_filt_len : 1) > s->ws.Fr - s->ws.F) return fail(PVGPU_ESTATE, "too many overlapping (dropped) slices; retrieve output more often");
     DevRows g{};
@@ -1286,20 +1360,19 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     g.out = s->d_out.as<float>(); g.out_stride = out_stride; g.out_base = out_base;
     s->ws.bind(pl, g);
     g.aux_base = k0;
-    if (pl.d.whisper) {
+    if (pl.d.whisper) {   // whisperSlice draws rand() channel-major per slice (:814-822): the next added * C * H values of this instance's generator
         const size_t n = (size_t)added * C * p.H;
-        std::vector<float> ph(n);
+        s->scratch.resize(n);
         const float two_pi = 2 * M_PI;
-        for (size_t i = 0; i < n; ++i) ph[i] = two_pi * (float)s->rng.next() / (float)2147483647;
+        for (size_t i = 0; i < n; ++i) s->scratch[i] = two_pi * (float)s->rng.next() / (float)2147483647;
         CU(pl.b_whisper.ensure(sizeof(float) * n));
-        CU(cudaMemcpyAsync(pl.b_whisper.p, ph.data(), sizeof(float) * n, cudaMemcpyHostToDevice, s->st));
-        CU(cudaStreamSynchronize(s->st));
+        if ((rc = pl.h2d(pl.b_whisper.p, s->scratch.data(), sizeof(float) * n, s->st))) return rc;
     }
     pl.apply_mode(g);   // after the whisper table has its final address
     if (pl.d.vocoder) {
         const int64_t clen = (int64_t)s->car_tail.size();
         CU(s->d_car.ensure(sizeof(float) * (size_t)std::max<int64_t>(clen, 1)));
-        if (clen) CU(cudaMemcpyAsync(s->d_car.p, s->car_tail.data(), sizeof(float) * clen, cudaMemcpyHostToDevice, s->st));
+        if ((rc = pl.h2d(s->d_car.p, s->car_tail.data(), sizeof(float) * clen, s->st))) return rc;
         CU(pl.b_carmag.ensure(sizeof(float) * (size_t)added * p.Hp));
         CU(pl.b_carph.ensure(sizeof(float) * (size_t)added * p.Hp));
         DevRows gc{};
@@ -1311,12 +1384,16 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     for (long k = k0; k < k0 + added; k += s->ws.F)
         if ((rc = pl.run_frames(g, k, (int)std::min<long>(s->ws.F, k0 + added - k), s->st))) return rc;
     CU(cudaGetLastError());
+    const float *h_out = nullptr;
     if (new_out > 0) {
-        s->h_stage.resize((size_t)C * new_out);
-        CU(cudaMemcpy2DAsync(s->h_stage.data(), sizeof(float) * new_out, s->d_out.p, sizeof(float) * out_stride, sizeof(float) * new_out, C, cudaMemcpyDeviceToHost, s->st));
+        float *pin = (float *)s->arena.take(sizeof(float) * (size_t)C * new_out);
+        if (!pin) { s->h_stage.resize((size_t)C * new_out); pin = s->h_stage.data(); }
+        CU(cudaMemcpy2DAsync(pin, sizeof(float) * new_out, s->d_out.p, sizeof(float) * out_stride, sizeof(float) * new_out, C, cudaMemcpyDeviceToHost, s->st));
+        h_out = pin;
     }
-    CU(cudaStreamSynchronize(s->st));
-    for (int c = 0; c < C && new_out > 0; ++c) s->fifo[c].insert(s->fifo[c].end(), s->h_stage.begin() + (size_t)c * new_out, s->h_stage.begin() + (size_t)(c + 1) * new_out);
+    CU(cudaStreamSynchronize(s->st));   // the call's only synchronisation
+    pl.staged_all = true;
+    for (int c = 0; c < C && new_out > 0; ++c) s->fifo[c].insert(s->fifo[c].end(), h_out + (size_t)c * new_out, h_out + (size_t)(c + 1) * new_out);
     // forget what no later slice can need
     const long k_next = k0 + added;
     const int64_t new_base = (int64_t)k_next * p.hop;
@@ -1324,7 +1401,11 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
     for (int c = 0; c < C; ++c) s->tail[c].erase(s->tail[c].begin(), s->tail[c].begin() + dropn);
     if (pl.d.vocoder) s->car_tail.erase(s->car_tail.begin(), s->car_tail.begin() + std::min<int64_t>(dropn, (int64_t)s->car_tail.size()));
     s->in_base += dropn;
-    {
+    if (pl.fused) {
+        // the fused kernel carries the unfinished accumulator and the resampler history on the device: the schedule and the
+        // normalisers before the next slice are never needed again, so a call uploads only what it added
+        sc.trim(k_next, sc.ola_total());
+    } else {
         // keep every record / normaliser a later slice can still reach: the slices holding the last filt_len-1 samples of
         // the normalised stream (resampler history) and the frames overlapping them
         const auto &recs = sc.recs();

@@ -42,7 +42,7 @@ constexpr int kTokenBarrier0 = 8;   // token barriers 8..15 (frame_sync uses 1..
 // 2 = the same + formant / gender frequency warp.  kOV8: the interpolated resampler with oversampling 8 (every ratio within
 // an octave); otherwise the resampler variant is chosen at run time (direct table, oversampling 1/2/4, or none).
 template <int N, int kPre, bool kOV8>
-__global__ void __launch_bounds__(FusedShape<N>::kThreads, N <= 2048 ? 3 : (N == 4096 ? 2 : 1)) k_synth_ola(const DevPlan p, const DevRows g, const FusedArgs a) {
+__global__ void __launch_bounds__(FusedShape<N>::kThreads, N <= 2048 ? 3 : 2) k_synth_ola(const DevPlan p, const DevRows g, const FusedArgs a) {
     using FS = FusedShape<N>;
     constexpr int NC = N / 2;
     using S = FftShape<NC>;
@@ -170,12 +170,12 @@ __global__ void __launch_bounds__(FusedShape<N>::kThreads, N <= 2048 ? 3 : (N ==
         {
             const int x_shift = (int)(s_hdr.u_lo - (res_base - HL)) - kResPad;
             const int64_t orow = row_out + s_hdr.out_first, out_limit = row_limit - s_hdr.out_first;
-            if (kOV8) resample_run<8>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, L);
-            else if (!quad) resample_run<0>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, L);
-            else if (p.rs_oversample == 4) resample_run<4>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, L);
-            else if (p.rs_oversample == 2) resample_run<2>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, L);
-            else if (p.rs_oversample == 8) resample_run<8>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, L);
-            else resample_run<1>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, L);
+            if (kOV8) resample_run<8>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, a.rs_steps, L);
+            else if (!quad) resample_run<0>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, a.rs_steps, L);
+            else if (p.rs_oversample == 4) resample_run<4>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, a.rs_steps, L);
+            else if (p.rs_oversample == 2) resample_run<2>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, a.rs_steps, L);
+            else if (p.rs_oversample == 8) resample_run<8>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, a.rs_steps, L);
+            else resample_run<1>(p, g, s_hdr, s_quad, s_in, x_shift, orow, out_limit, a.rs_ent, a.rs_frac, a.rs_steps, L);
         }
         __syncthreads();
         // ---- keep the last HL normalised samples as the next run's history ----
@@ -230,7 +230,7 @@ static size_t fused_smem(const DevPlan &p, const FusedArgs &a) {
 
 // Shape of the fused kernel for a schedule: frames per run (a multiple of the frames in flight that divides
 // frames_per_chunk), ring length, resampler window.  Returns false when no run length fits the shared-memory budget.
-bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_consumed, int max_out, size_t smem_limit, FusedArgs *out) {
+bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_consumed, int max_out, size_t smem_limit, int force_run, FusedArgs *out) {
     const int G = fused_frames_in_flight(p.N);
     if (G == 0) return false;
     const int L = p.rs_active ? (int)p.rs_filt_len : 0;
@@ -241,6 +241,7 @@ bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_c
     // padding of the resampler's work lists, shorter ones keep the ring small
     for (int run = G; run <= 64; run += G) {
         if (frames_per_chunk % run) continue;
+        if (force_run > 0 && run != force_run) continue;   // PVGPU_FUSED_RUN: tuning experiments
         FusedArgs a{};
         a.run = run;
         a.hist_len = p.rs_active ? L + 8 : 0;
@@ -250,9 +251,9 @@ bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_c
         if (p.rs_active && (run * max_consumed + L + 8 + kResPad >= 65536 || run * max_out >= 65535)) break;
         const size_t sm = fused_smem(p, a);
         if (sm > smem_limit) break;
-        const int target = p.N <= 2048 ? 3 : (p.N == 4096 ? 2 : 1);
+        const int target = p.N <= 2048 ? 3 : 2;   // resident CTAs per SM the launch bounds aim for
         const size_t per_cta = ((size_t)227 * 1024) / target - 1024;
-        if (found && sm > per_cta) break;     // do not trade a resident CTA for a longer run
+        if (found && sm > per_cta && force_run <= 0) break;     // do not trade a resident CTA for a longer run
         best = a;
         found = true;
     }

@@ -794,7 +794,7 @@ struct OlaTables {
 template <int OV>   // sinc-table oversampling of the interpolated resampler mode; 0 = direct table or no resampler
 __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const DevRows g, const SliceRec *__restrict__ recs, const float *__restrict__ norm,
                                                       int64_t norm_base, long recs_base, long k0, int nf, int run, int max_in, const ResampleRun *__restrict__ runs,
-                                                      const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, long run_origin) {
+                                                      const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac, const unsigned *__restrict__ rs_steps, long run_origin) {
     extern __shared__ float4 smem4[];
     __shared__ OlaTables T;
     __shared__ ResampleRun s_hdr;
@@ -913,7 +913,7 @@ __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const 
     const int64_t out_limit = g.n_out[row] - hdr.out_first;
     const int in_shift = (int)(hdr.u_lo - u_lo) - kResPad;   // hdr.u_lo == u_lo; entries are biased by kResPad
     (void)out_first;
-    resample_run<OV>(p, g, hdr, s_quad, s_in, in_shift, orow, out_limit, rs_ent, rs_frac, L);
+    resample_run<OV>(p, g, hdr, s_quad, s_in, in_shift, orow, out_limit, rs_ent, rs_frac, rs_steps, L);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1085,13 +1085,13 @@ int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out) {
 
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
                          long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
-                         long run_origin, cudaStream_t st) {
+                         const unsigned *rs_steps, long run_origin, cudaStream_t st) {
     const int L = p.rs_active ? (int)p.rs_filt_len : 1;
     const bool quad = p.rs_active && !p.rs_direct;
     const int max_in = ((run * max_consumed + L + 8) + 3) & ~3;
     const size_t sm = (quad ? sizeof(float4) * (size_t)p.rs_table_len : 0) + sizeof(float) * (size_t)(max_in + (p.rs_active ? L : 0));
     dim3 grid((nframes + run - 1) / run, g.rows);
-#define PV_OLA(OVV) k_ola_resample<OVV><<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, run_origin)
+#define PV_OLA(OVV) k_ola_resample<OVV><<<grid, 256, sm, st>>>(p, g, recs, norm, norm_base, recs_base, k0, nframes, run, max_in, runs, rs_ent, rs_frac, rs_steps, run_origin)
     if (!quad) PV_OLA(0);
     else if (p.rs_oversample == 8) PV_OLA(8);
     else if (p.rs_oversample == 4) PV_OLA(4);

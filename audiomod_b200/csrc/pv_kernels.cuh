@@ -90,7 +90,7 @@ void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag,
 // interpolation fraction of each entry (interpolated mode) or the table phase as raw bits (direct mode).
 constexpr int kMaxBuckets = 8;      // resampler table phases (oversample <= 8 at quality 4)
 constexpr int kResPerThread = 4;    // outputs a thread of k_ola_resample accumulates at once
-constexpr int kResBlock = 32 * kResPerThread;   // entries a warp takes per step; buckets are padded to this
+constexpr int kResBlock = 32 * kResPerThread;   // entries of a full warp step; the bank-aware ordering works on two of these at a time
 constexpr int kResPad = 1024;       // bias that keeps the packed tap-0 offset non-negative at the start of a stream
 struct ResampleRun {
     int64_t u_lo;        // first normalised-stream position the run reads (clipped to 0)
@@ -98,7 +98,9 @@ struct ResampleRun {
     int ent_off;         // offset of the run's entries in rs_ent / rs_frac
     int padded;          // entries including padding
     int start[kMaxBuckets + 1];
-    int pad[3];
+    int step_off;        // offset of the run's warp steps in rs_steps
+    int n_steps;         // step = entry offset within the run | (rows - 1) << 20 | table phase << 24, rows <= kResPerThread
+    int pad[1];
 };
 static_assert(sizeof(ResampleRun) == 72, "ResampleRun layout");
 
@@ -108,7 +110,7 @@ int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out);
 // be run_origin + a multiple of run), max_consumed = the largest number of normalised samples any slice contributes
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
                          long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
-                         long run_origin, cudaStream_t st);
+                         const unsigned *rs_steps, long run_origin, cudaStream_t st);
 // Fused inverse FFT + window + overlap-add + normalisation + resampler (k_synth_ola, pv_fused.cu): one CTA per row runs the
 // frames [k0, k0 + nf) of a chunk in order, `run` frames per round (a multiple of the frames it has in flight).
 struct FusedArgs {
@@ -119,11 +121,11 @@ struct FusedArgs {
     int acc_len;      // floats of the shared-memory accumulator ring: power of two >= N + (run - 1) * largest shift increment
     int in_len;       // floats of the resampler input window: hist_len + run * largest per-slice contribution (+ pad)
     int hist_len;     // filt_len + 8 normalised samples carried between rounds / launches (0 without resampler)
-    const ResampleRun *runs; const unsigned *rs_ent; const float *rs_frac; long run_origin;
+    const ResampleRun *runs; const unsigned *rs_ent; const float *rs_frac; const unsigned *rs_steps; long run_origin;
     const float *car_mag, *car_phase;   // vocoder carrier spectra or null
 };
 int fused_frames_in_flight(int N);   // 0: this FFT size has no fused kernel
-bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_consumed, int max_out, size_t smem_limit, FusedArgs *out);
+bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_consumed, int max_out, size_t smem_limit, int force_run, FusedArgs *out);
 cudaError_t launch_synth_ola(const DevPlan &p, const DevRows &g, const FusedArgs &a, cudaStream_t st);
 
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
