@@ -319,7 +319,10 @@ struct Pipeline {
     // The phase-locked core (coremode 1) of the shift / stretch / formant / gender modes also runs on Cartesian spectra
     // (pv_lock.cuh): locking a region is one rotation of its bins, and the analysis phase is only ever needed at the peaks.
     bool cartesian_lock() const {
-        return d.cfg.coremode == 1 && !(d.robotic || d.whisper || d.vocoder || d.constant_mode);
+        if (!(d.cfg.coremode == 1 && !(d.robotic || d.whisper || d.vocoder || d.constant_mode))) return false;
+        // the split kernels keep per-channel spectra and maps of a stream in shared memory: with many channels at large FFT
+        // sizes that exceeds the 200 KB opt-in, and the serial polar core (k_phase_lock_t) takes over
+        return lock_smem_bytes(p, d.cfg.channels, max_peaks()) <= (size_t)200 * 1024;
     }
     bool cartesian() const {
         const bool templated = p.N == 512 || p.N == 1024 || p.N == 2048 || p.N == 4096 || p.N == 8192;
@@ -640,6 +643,18 @@ static int halo_of(const std::vector<SliceRec> &recs, long recs_base, int hist_l
     return (int)h;
 }
 
+// Largest number of slices before slice k whose normalised samples the resampler's history (hist_len - 1 samples) reaches.
+static int hist_slices_of(const std::vector<SliceRec> &recs, int hist_len) {
+    long h = 0;
+    for (size_t i = 0; i < recs.size(); ++i) {
+        size_t kh = i;
+        const int64_t u_lo = recs[i].res_off + recs[i].rs_last - hist_len + 1;
+        while (kh > 0 && recs[kh].res_off > u_lo) --kh;
+        h = std::max<long>(h, (long)(i - kh));
+    }
+    return (int)h;
+}
+
 }  // namespace pvgpu
 
 using namespace pvgpu;
@@ -706,6 +721,12 @@ struct pvgpu_batch {
     int prepare_runs() {
         if (run_for_chunk == frames_per_chunk) return PVGPU_OK;
         pl.plan_fused(frames_per_chunk, pl.max_consumed, pl.max_out);   // shape of the fused kernel for this chunk size (or the split kernels)
+        if (!pl.fused) {   // k_ola_resample's per-CTA tables: frames overlapping a run, slices holding the resampler history before it
+            const int hist = hist_slices_of(pl.h_recs, pl.p.rs_active ? (int)pl.p.rs_filt_len : 1);
+            if (hist + 2 > ola_max_table_slices() - 1)
+                return fail(PVGPU_EINVAL, "the resampler history spans %d slices, more than the split kernels' tables hold (the fused kernel has no such limit)", hist);
+            pl.ola_run = std::min(pl.ola_run, ola_max_table_slices() - hist - 1);
+        }
         if (!pl.fused && halo + pl.ola_run > 90) pl.ola_run = std::max(1, 90 - halo);
         if (!pl.fused && halo + pl.ola_run > 90)
             return fail(PVGPU_EINVAL, "stretch/pitch ratio too extreme for the split kernels: %d overlapping frames (the fused kernel has no such limit)", halo);

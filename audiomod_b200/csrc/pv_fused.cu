@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(FusedShape<N>::kThreads, N <= 2048 ? 3 : 2) k_
     constexpr int NC = N / 2;
     using S = FftShape<NC>;
     constexpr int T = FS::T, G = FS::G, U = FS::U, UT = FS::UT, FU = FS::FU, kThreads = FS::kThreads;
-    extern __shared__ float4 smem4[];
+    extern __shared__ __align__(16) float4 smem4[];
     __shared__ ResampleRun s_hdr;
     const int row = blockIdx.x, tid = threadIdx.x;
     const int group = tid / T, t = tid % T, unit = tid / UT;

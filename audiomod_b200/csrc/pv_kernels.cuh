@@ -106,6 +106,11 @@ static_assert(sizeof(ResampleRun) == 72, "ResampleRun layout");
 
 // largest run (slices per CTA) not above `run` that the packed entries and the CTA tables can hold
 int ola_run_limit(const DevPlan &p, int run, int max_consumed, int max_out);
+// sizes of k_ola_resample's per-CTA tables: slices (run + resampler history) and the frames overlapping them
+int ola_max_table_slices();
+int ola_max_table_frames();
+// dynamic shared memory of the phase-locked core's kernels on Cartesian spectra for C channels per stream
+size_t lock_smem_bytes(const DevPlan &p, int channels, int maxpk);
 // overlap-add + normalisation (+ resampler when p.rs_active); `run` consecutive slices per CTA starting at k0 (which must
 // be run_origin + a multiple of run), max_consumed = the largest number of normalised samples any slice contributes
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
