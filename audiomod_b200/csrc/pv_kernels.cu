@@ -1009,7 +1009,7 @@ template <int N> static void launch_analyse_t(const DevPlan &p, const DevRows &g
     const int grid = (total + G - 1) / G, block = T >= 256 ? T : 256;
     const size_t sm = sizeof(float2) * G * S::kPadded;
     static const bool bulk = [] { const char *e = std::getenv("PVGPU_ANALYSE_BULK"); return e && e[0] == '1'; }();
-    if (bulk && g.spec && !g.fmt && (N * sizeof(float) + 16 <= sizeof(float2) * S::kPadded)) {
+    if (bulk && g.spec && !g.fmt && (N * sizeof(float) + 16 <= sizeof(float2) * S::kPadded) && (sizeof(float2) * S::kPadded) % 16 == 0) {
         // the over-fetch stays inside the row: rows are in_stride apart and both the base and the stride are 16-byte multiples
         if ((reinterpret_cast<uintptr_t>(g.in) & 15) == 0 && (g.in_stride & 3) == 0) {
             k_analyse_t<N, false, true, true><<<grid, block, sm + 8 * G + 8, st>>>(p, g, k0, nframes, total);

@@ -65,6 +65,7 @@ struct DevRows {
     // fused inverse FFT + overlap-add + resampler (pv_fused.cu): what a row carries from one launch to the next
     float *ola_tail;          // [rows][N]: the unfinished part of the overlap-add accumulator (from the next slice's position on)
     float *res_hist;          // [rows][filt_len + 8]: the last normalised samples (resampler history), zeros before the stream
+    int zero_mask;            // always 0; an operand the compiler cannot fold, used to tie load batches together (pv_synth.cuh)
     long aux_base;            // slice index of element 0 of the whisper table / carrier spectra
     int spec;                 // 0: spectra are (mag, phase); 1: Cartesian (re in mag[], im in phase[]) -- modes that never use the
                               //    analysis phase (robotic, whisper, vocoder, constant) and the phase-locked core of the plain

@@ -133,13 +133,33 @@ __device__ __forceinline__ void synth_prepass_lock(const DevPlan &p, const DevRo
             hi[u] = make_float2(gre[sh[u]], gim[sh[u]]);
         }
         if (locked) {
+            // Two dependent gathers per bin (bin -> region -> rotation).  All region loads are issued first, then all rotation
+            // loads, unconditionally from clamped indices, and the exceptions are patched afterwards.  Left to itself ptxas may
+            // issue each rotation load right behind its own region load to save registers, which serialises the chains
+            // (measured after a refactoring that did not change a single instruction of this loop, only their order:
+            // long-scoreboard stalls 5.9 -> 12.2 per issue, 50 -> 72 ms); the `tie` below takes that freedom away.  Bin NC (Nyquist) is not part of any region -- the reference leaves its phase alone;
+            // without the warp table only the upper bin of kk == 0 is NC, with it a low target bin can have it as source too
+            // (factor > 2).
+            unsigned ml[U], mh[U], all = 0;
             float2 cl[U], ch[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                // bin NC (Nyquist) is not part of any region: the reference leaves its phase alone.  With the warp table a
-                // low target bin can also have the Nyquist bin as its source (factor > 2), so both gathers are guarded.
-                cl[u] = sl[u] >= NC ? make_float2(1.f, 0.f) : lcsn[lmap[sl[u]]];
-                ch[u] = sh[u] >= NC ? make_float2(1.f, 0.f) : lcsn[lmap[sh[u]]];
+                ml[u] = lmap[kWarp ? min(sl[u], NC - 1) : sl[u]];
+                mh[u] = lmap[min(sh[u], NC - 1)];
+                all |= ml[u] | mh[u];
+            }
+            // every rotation address depends on every region index (through a mask that is zero at run time, which the compiler
+            // cannot know): the 2U region loads are all in flight before the first rotation load can issue
+            const unsigned tie = all & (unsigned)g.zero_mask;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cl[u] = lcsn[ml[u] + tie];
+                ch[u] = lcsn[mh[u] + tie];
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (kWarp && sl[u] >= NC) cl[u] = make_float2(1.f, 0.f);
+                if (sh[u] >= NC) ch[u] = make_float2(1.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {

@@ -27,7 +27,8 @@ data = [r for r in b["rows"][1:] if len(r) > ix["Instructions Executed"]]
 # mangled-name fragment: take the template arguments into account through the demangled name's order of appearance
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "audiomod_b200", "libpvgpu.so")], cwd=tmp, capture_output=True)
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, "pv_kernels.sm_100a.cubin")], capture_output=True, text=True).stdout
+dis = "".join(subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, c)], capture_output=True, text=True).stdout
+              for c in sorted(os.listdir(tmp)) if c.endswith(".cubin"))
 funcs, name, line = defaultdict(list), None, None
 for l in dis.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
