@@ -517,7 +517,8 @@ struct Pipeline {
         if (fused_frames_in_flight(p.N) == 0) return false;
         FusedArgs a{};
         const char *fr = std::getenv("PVGPU_FUSED_RUN");
-        if (!fused_plan(p, frames_per_chunk, max_shift, max_shift, max_out_bound, (size_t)200 * 1024, fr ? std::atoi(fr) : 0, &a)) return false;
+        const char *ws = std::getenv("PVGPU_FUSED_WS");
+        if (!fused_plan(p, frames_per_chunk, max_shift, max_shift, max_out_bound, (size_t)200 * 1024, fr ? std::atoi(fr) : 0, ws && ws[0] == '1', &a)) return false;
         fa = a;
         fused = true;
         return true;

@@ -955,7 +955,7 @@ __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const 
     const int64_t out_limit = g.n_out[row] - hdr.out_first;
     const int in_shift = (int)(hdr.u_lo - u_lo) - kResPad;   // hdr.u_lo == u_lo; entries are biased by kResPad
     (void)out_first;
-    resample_run<OV>(p, g, hdr, s_quad, s_in, in_shift, orow, out_limit, rs_ent, rs_frac, rs_steps, L);
+    resample_run<OV>(p, g, hdr, s_quad, s_in, in_shift, orow, out_limit, rs_ent, rs_frac, rs_steps, L, threadIdx.x >> 5, blockDim.x >> 5);
 }
 
 // ------------------------------------------------------------------------------------------------

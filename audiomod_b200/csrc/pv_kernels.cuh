@@ -127,11 +127,12 @@ struct FusedArgs {
     int acc_len;      // floats of the shared-memory accumulator ring: power of two >= N + (run - 1) * largest shift increment
     int in_len;       // floats of the resampler input window: hist_len + run * largest per-slice contribution (+ pad)
     int hist_len;     // filt_len + 8 normalised samples carried between rounds / launches (0 without resampler)
+    int ws;           // 1: warp-specialised kernel (k_synth_ola_ws: producer warps + resampler warps, two input windows)
     const ResampleRun *runs; const unsigned *rs_ent; const float *rs_frac; const unsigned *rs_steps; long run_origin;
     const float *car_mag, *car_phase;   // vocoder carrier spectra or null
 };
 int fused_frames_in_flight(int N);   // 0: this FFT size has no fused kernel
-bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_consumed, int max_out, size_t smem_limit, int force_run, FusedArgs *out);
+bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_consumed, int max_out, size_t smem_limit, int force_run, bool want_ws, FusedArgs *out);
 cudaError_t launch_synth_ola(const DevPlan &p, const DevRows &g, const FusedArgs &a, cudaStream_t st);
 
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);

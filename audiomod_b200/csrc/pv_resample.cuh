@@ -89,16 +89,15 @@ __device__ __forceinline__ void resample_step(const DevPlan &p, const DevRows &g
 }
 
 // s_x[i + x_shift] is the normalised-stream sample an entry's packed tap-0 position i refers to; out positions are relative
-// to orow (element index of the run's first output in g.out); outputs at or beyond out_limit are not stored.  The warps of
-// the CTA take the run's steps round-robin (the host lists the long steps first).
+// to orow (element index of the run's first output in g.out); outputs at or beyond out_limit are not stored.  The `nwarp`
+// warps that call this (warp = 0..nwarp-1) take the run's steps round-robin (the host lists the long steps first).
 template <int OV>   // sinc-table oversampling of the interpolated mode; 0 = direct table
 __device__ __forceinline__ void resample_run(const DevPlan &p, const DevRows &g, const ResampleRun &hdr, const float4 *s_quad, const float *s_x, int x_shift,
                                              int64_t orow, int64_t out_limit, const unsigned *__restrict__ rs_ent, const float *__restrict__ rs_frac,
-                                             const unsigned *__restrict__ rs_steps, int L) {
+                                             const unsigned *__restrict__ rs_steps, int L, int warp, int nwarp) {
     const unsigned *__restrict__ ent_tab = rs_ent + hdr.ent_off;
     const float *__restrict__ frac_tab = rs_frac + hdr.ent_off;
     const unsigned *__restrict__ steps = rs_steps + hdr.step_off;
-    const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     for (int s = warp; s < hdr.n_steps; s += nwarp) {
         const unsigned desc = __ldg(&steps[s]);   // warp-uniform
         const int first = (int)(desc & 0xfffffu), rows = (int)((desc >> 20) & 7u) + 1, bucket = (int)(desc >> 24);
