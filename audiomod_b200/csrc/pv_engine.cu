@@ -131,7 +131,10 @@ struct Pipeline {
     int ola_run = 16;       // slices per CTA of k_ola_resample (upper bound)
     // fused inverse FFT + overlap-add + resampler (pv_fused.cu) instead of k_synthesise_t -> frame ring -> k_ola_resample
     bool fused = false;
-    bool allow_fused = true;    // PVGPU_FUSED=0 or pvgpu_batch_tune / pvgpu_tune_stream select the split kernels (A/B runs, tests)
+    // Which resynthesis back end: -1 automatic (the split kernels, which are the faster ones on B200 -- profiles/r02_summary.md --
+    // unless the schedule overlaps more frames / history slices than their per-CTA tables hold, then the fused kernel, which
+    // has no such limit), 0 split only, 1 fused wherever the FFT size has one.  PVGPU_FUSED=0/1 overrides for every instance.
+    int fused_pref = -1;
     FusedArgs fa{};             // run / ring / window shape; per-launch fields are filled in run_synth_ola
     // host copy of the uploaded records + the resampler work lists built from them (ResampleRun, pv_kernels.cuh)
     std::vector<SliceRec> h_recs;
@@ -510,10 +513,12 @@ struct Pipeline {
     }
     // Decide whether launches of `frames_per_chunk` frames use the fused kernel, and its shape.  max_shift bounds the
     // per-slice accumulator advance (and so the resampler's per-slice input).
-    bool plan_fused(int frames_per_chunk, int max_shift, int max_out_bound) {
+    // split_ok: the split kernels can run this schedule (their table limits hold)
+    bool plan_fused(int frames_per_chunk, int max_shift, int max_out_bound, bool split_ok) {
         fused = false;
         const char *env = std::getenv("PVGPU_FUSED");
-        if (!allow_fused || (env && env[0] == '0')) return false;
+        const int pref = (env && (env[0] == '0' || env[0] == '1')) ? env[0] - '0' : fused_pref;
+        if (pref == 0 || (pref < 0 && split_ok)) return false;
         if (fused_frames_in_flight(p.N) == 0) return false;
         FusedArgs a{};
         const char *fr = std::getenv("PVGPU_FUSED_RUN");
@@ -721,7 +726,10 @@ struct pvgpu_batch {
     int run_for_chunk = 0;   // frames_per_chunk the resampler work lists were built for
     int prepare_runs() {
         if (run_for_chunk == frames_per_chunk) return PVGPU_OK;
-        pl.plan_fused(frames_per_chunk, pl.max_consumed, pl.max_out);   // shape of the fused kernel for this chunk size (or the split kernels)
+        // k_ola_resample's per-CTA tables bound the frames overlapping a run and the slices holding the resampler history
+        const int hist_all = hist_slices_of(pl.h_recs, pl.p.rs_active ? (int)pl.p.rs_filt_len : 1);
+        const bool split_ok = hist_all + 2 <= ola_max_table_slices() - 1 && halo + 1 <= 90;
+        pl.plan_fused(frames_per_chunk, pl.max_consumed, pl.max_out, split_ok);   // fused kernel (and its shape) or the split kernels
         if (!pl.fused) {   // k_ola_resample's per-CTA tables: frames overlapping a run, slices holding the resampler history before it
             const int hist = hist_slices_of(pl.h_recs, pl.p.rs_active ? (int)pl.p.rs_filt_len : 1);
             if (hist + 2 > ola_max_table_slices() - 1)
@@ -908,7 +916,7 @@ int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, i
 
 int pvgpu_batch_set_fused(pvgpu_batch *b, int enable) {
     if (!b) return fail(PVGPU_EINVAL, "null batch");
-    b->pl.allow_fused = enable != 0;
+    b->pl.fused_pref = enable < 0 ? -1 : (enable != 0 ? 1 : 0);
     b->run_for_chunk = 0;   // re-plan the launches at the next run
     return PVGPU_OK;
 }
@@ -1463,7 +1471,11 @@ int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out) {
         const int nominal = fixed ? (d.int_ratio && !(d.robotic || d.whisper || d.vocoder || d.constant_mode) ? (int)(size_t)(d.hop * d.hs) : d.hop)
                                   : (int)std::lrint(2.0 * d.hop * (double)d.hs) + 2;
         const int out_bound = (int)std::ceil(nominal * (double)(s->pl.p.rs_active ? d.rs.ratio : 1.f)) + 2;
-        s->pl.plan_fused(pvgpu_stream::kF, std::max(nominal, 1), out_bound);
+        // split kernels: the instance's frame ring holds `halo` frames before a chunk; dozens of overlapping frames (extreme
+        // stretch ratios) or a resampler history of many slices need the fused kernel
+        const int min_shift = std::max(1, fixed ? nominal : (int)std::lrint(0.5 * d.hop * (double)d.hs));
+        const int overlap = (d.N + min_shift - 1) / min_shift + (s->pl.p.rs_active ? ((int)d.rs.filt_len + min_shift - 1) / min_shift : 0) + 2;
+        s->pl.plan_fused(pvgpu_stream::kF, std::max(nominal, 1), out_bound, overlap + 8 <= halo && overlap + 8 <= ola_max_table_slices() - 1);
     }
     if ((rc = s->ws.ensure(s->pl, cfg->channels, pvgpu_stream::kF, halo))) return rc;
     if ((rc = s->ws.reset_state(s->pl, s->st))) return rc;

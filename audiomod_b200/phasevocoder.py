@@ -180,9 +180,10 @@ class PhaseVocoderBatch:
         self.run_host_rows(in_rows, out_rows, fmt)
         return outs
 
-    def set_fused(self, enable: bool = True):
-        """Fused inverse-FFT + overlap-add + resampler kernel (default) or the split kernels; bit-identical results."""
-        check(_lib.lib().pvgpu_batch_set_fused(self._h, int(bool(enable))))
+    def set_fused(self, enable=True):
+        """True: the fused inverse-FFT + overlap-add + resampler kernel; False: the split kernels; None: automatic (split unless the
+        stretch ratio exceeds their table limits).  Bit-identical results either way."""
+        check(_lib.lib().pvgpu_batch_set_fused(self._h, -1 if enable is None else int(bool(enable))))
 
     KERNEL_KINDS = ("analyse", "phase_core", "synthesise", "ola_resample", "synth_ola", "fixed_phase", "lock_peaks", "lock_chain")
 

@@ -126,10 +126,12 @@ int pvgpu_batch_kernel_times(pvgpu_batch *b, double *ms /*[PVGPU_KINDS]*/, int64
  * and equal-length batches in evenly spaced host rows are pipelined along time; an explicit value selects pipelining
  * across row groups); how many row groups are in flight at once (1..4; each has its own stream, workspace and staging) */
 int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, int contexts);
-/* Resynthesis back end: 1 (default) = the fused inverse-FFT + overlap-add + resampler kernel with the accumulator in shared
- * memory wherever the FFT size has one (512..8192); 0 = the split kernels (inverse FFT -> frame ring in HBM -> overlap-add +
- * resampler).  Both produce bit-identical samples (tests/test_gpu_fused.py); the switch exists for A/B measurements.  The
- * environment variable PVGPU_FUSED=0 does the same for every instance, including streaming ones. */
+/* Resynthesis back end: 0 = the split kernels (inverse FFT -> frame ring in HBM -> overlap-add + resampler); 1 = the fused
+ * inverse-FFT + overlap-add + resampler kernel with the accumulator in shared memory wherever the FFT size has one
+ * (512..8192); -1 (default) = automatic: the split kernels -- measured faster on B200, profiles/r02_summary.md -- unless the
+ * stretch ratio overlaps more frames than their per-CTA tables hold, then the fused kernel, which has no such limit.  Both
+ * produce bit-identical samples (tests/test_gpu_fused.py).  The environment variable PVGPU_FUSED=0/1 overrides the choice for
+ * every instance, including streaming ones. */
 int pvgpu_batch_set_fused(pvgpu_batch *b, int enable);
 
 /* ---------------------------------------------------------------------------------------------
