@@ -184,6 +184,8 @@ struct Pipeline {
         if (d.hop < 1 || d.hop > d.N) return fail(PVGPU_EINVAL, "derived hop %d invalid for fft size %d", d.hop, d.N);
         t = make_tables(d.N, d.hop);
         if ((int)t.radix.size() > kMaxStages) return fail(PVGPU_EINVAL, "fft size too large");
+        if (d.cepstral && !(d.N == 512 || d.N == 1024 || d.N == 2048 || d.N == 4096 || d.N == 8192))
+            return fail(PVGPU_EINVAL, "the cepstral modes need an FFT size of 512..8192 (got %d)", d.N);
         CU(configure_kernels());
         p.N = d.N; p.H = d.H; p.half = d.N / 2; p.nc = d.N / 2; p.hop = d.hop;
         p.Hp = (d.H + 3) & ~3;
@@ -504,6 +506,11 @@ struct Pipeline {
             sp = span_begin(7, st); launch_lock_chain(p, g, nf, st); span_end(sp, st); ++launches;
         } else if (!d.vocoder && !d.constant_mode) {
             sp = span_begin(1, st); launch_phase_core(p, g, d.cfg.coremode, recs, recs_base, k0, nf, st); span_end(sp, st); ++launches;
+        }
+        if (d.cepstral) {   // optional modes 8 / 9: whiten by the cepstral envelope, put the warped envelope back (pv_cepstral.cu)
+            sp = span_begin(5, st);
+            if (!launch_cepstral(p, g, d.env_comp, nf, st)) return fail(PVGPU_EINVAL, "the cepstral modes need an FFT size of 512..8192");
+            span_end(sp, st); ++launches;
         }
         if (fused) return PVGPU_OK;   // the inverse FFT is part of run_synth_ola
         sp = span_begin(2, st);
@@ -1534,7 +1541,7 @@ int pvgpu_retrieve(pvgpu_stream *s, float *const *out, int n) {
 int pvgpu_process_block(pvgpu_stream *s, float *const *buf, int n, int *ready) {
     if (!s || !ready) return fail(PVGPU_EINVAL, "bad argument");
     const int m = s->cfg.mode;
-    if (m == PVGPU_NORMAL_STRETCH || m < -1 || m > 7) { *ready = 1; return PVGPU_OK; }  // processBlock routes neither (phasevocoder.cc:133-146)
+    if (m == PVGPU_NORMAL_STRETCH || m < -1 || m > PVGPU_FORMANT_CEPSTRAL) { *ready = 1; return PVGPU_OK; }  // processBlock routes neither (phasevocoder.cc:133-146)
     int rc = pvgpu_process(s, buf, n);
     if (rc) return rc;
     if (s->num_res >= n) {  // processBlockNormal, phasevocoder.cc:156-183

@@ -135,6 +135,8 @@ int fused_frames_in_flight(int N);   // 0: this FFT size has no fused kernel
 bool fused_plan(const DevPlan &p, int frames_per_chunk, int max_shift, int max_consumed, int max_out, size_t smem_limit, int force_run, bool want_ws, FusedArgs *out);
 cudaError_t launch_synth_ola(const DevPlan &p, const DevRows &g, const FusedArgs &a, cudaStream_t st);
 
+// cepstral spectral-envelope modification of the chunk's spectra in place (pv_cepstral.cu); false: no kernel for this FFT size
+bool launch_cepstral(const DevPlan &p, const DevRows &g, float env_comp, int nframes, cudaStream_t st);
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
 

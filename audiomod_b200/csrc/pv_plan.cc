@@ -107,11 +107,11 @@ static void build_resampler(ResamplerSpec &rs, float ratio) {
 Derived derive(const Config &cfg) {
     Derived d;
     d.cfg = cfg;
-    d.valid_mode = cfg.mode >= -1 && cfg.mode <= 7;
+    d.valid_mode = cfg.mode >= -1 && cfg.mode <= kFormantCepstral;
     float time_ratio = cfg.time_ratio;
     float pitch_scale = cfg.pitch_semitones != 0 ? (float)std::pow(2.0, cfg.pitch_semitones / 12) : 1.0f;
-    d.gender = cfg.mode == kGender;
-    d.formant = cfg.mode == kFormant;
+    d.gender = cfg.mode == kGender || cfg.mode == kGenderCepstral;
+    d.formant = cfg.mode == kFormant || cfg.mode == kFormantCepstral;
     d.robotic = cfg.mode == kRobotic;
     d.whisper = cfg.mode == kWhisper;
     d.vocoder = cfg.mode == kVocRosen || cfg.mode == kVocChord;
@@ -150,6 +150,12 @@ Derived derive(const Config &cfg) {
     if (d.formant && pitch_scale != 1.0) d.freq_comp = pitch_scale;
     if (d.gender && pitch_scale != 1.0) d.freq_comp = pitch_scale > 1 ? (float)(0.85 * pitch_scale) : (float)(1.17 * pitch_scale);
     else if (d.gender) d.freq_comp = (float)0.8;
+    if ((cfg.mode == kGenderCepstral || cfg.mode == kFormantCepstral) && pitch_scale != 1.0) {
+        // the cepstral variants of maleToFemale / femaleToMale / formantPreserveSlice (:824-840 with the comments swapped)
+        d.freq_comp = 0.f;
+        d.cepstral = true;
+        d.env_comp = cfg.mode == kFormantCepstral ? 1.f : (pitch_scale > 1 ? 0.85f : 1.17f);
+    }
     d.fixed_gain = pitch_scale > 1 ? pitch_scale : 1 / pitch_scale;
     d.rs.active = pitch_scale != 1.0;
     if (d.rs.active) build_resampler(d.rs, (float)(1.0 / pitch_scale));

@@ -26,7 +26,9 @@
 
 namespace pvgpu {
 
-enum Mode { kConstant = -1, kShift = 0, kGender = 1, kFormant = 2, kVocRosen = 3, kVocChord = 4, kStretch = 5, kRobotic = 6, kWhisper = 7 };
+enum Mode { kConstant = -1, kShift = 0, kGender = 1, kFormant = 2, kVocRosen = 3, kVocChord = 4, kStretch = 5, kRobotic = 6, kWhisper = 7,
+            // extensions (not reference modes): gender / formant with the cepstral envelope routine the reference keeps commented out
+            kGenderCepstral = 8, kFormantCepstral = 9 };
 
 struct Config {
     int sample_rate = 44100, channels = 1;
@@ -70,6 +72,8 @@ struct Derived {
     bool valid_mode = true;
     bool int_ratio = false;
     float freq_comp = 0.f;   // 0: no frequency-axis warp
+    bool cepstral = false;   // modes 8 / 9: formantShiftSlice (phasevocoderprocess.cc:925-999) instead of freqCompSlice
+    float env_comp = 1.f;    //   its envelope warp factor (:824-840: 1 formant, 0.85 male->female, 1.17 female->male)
     float fixed_gain = 1.f;
     ResamplerSpec rs;
 };

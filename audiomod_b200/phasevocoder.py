@@ -18,6 +18,8 @@ from ._lib import Config, Info, check
 # mode / coremode constants, include/dafx/phasevocoder.h:22-36
 CONSTANT, NORMAL_SHIFT, GENDER_CHANGE, FORMANT_PRESERVE = -1, 0, 1, 2
 VOCODER_ROSENBERG, VOCODER_CHORD, NORMAL_STRETCH, ROBOTIC, WHISPER = 3, 4, 5, 6, 7
+# extensions (include/pvgpu.h): the reference's commented-out cepstral envelope routine instead of the nearest-bin warp
+GENDER_CEPSTRAL, FORMANT_CEPSTRAL = 8, 9
 NORMAL_PV, PHASE_LOCKED, INT_RATIO = 0, 1, 2
 
 _fp = C.POINTER(C.c_float)

@@ -27,7 +27,12 @@ enum { PVGPU_OK = 0, PVGPU_EINVAL = 1, PVGPU_ECUDA = 2, PVGPU_ENOMEM = 3, PVGPU_
 
 /* mode / coremode values: include/dafx/phasevocoder.h:22-36 */
 enum { PVGPU_CONSTANT = -1, PVGPU_NORMAL_SHIFT = 0, PVGPU_GENDER_CHANGE = 1, PVGPU_FORMANT_PRESERVE = 2,
-       PVGPU_VOCODER_ROSENBERG = 3, PVGPU_VOCODER_CHORD = 4, PVGPU_NORMAL_STRETCH = 5, PVGPU_ROBOTIC = 6, PVGPU_WHISPER = 7 };
+       PVGPU_VOCODER_ROSENBERG = 3, PVGPU_VOCODER_CHORD = 4, PVGPU_NORMAL_STRETCH = 5, PVGPU_ROBOTIC = 6, PVGPU_WHISPER = 7,
+       /* Extensions, not reference modes: gender change / formant-preserving shift with the cepstral spectral-envelope routine
+        * (formantShiftSlice, src/phasevocoder/phasevocoderprocess.cc:925-999 + FFT::inverseCepstral, FFT.cc:2723-2733) that the
+        * reference keeps commented out in favour of freqCompSlice (:824-840).  They compute what the reference computes with
+        * those comments swapped back; FFT sizes 512..8192. */
+       PVGPU_GENDER_CEPSTRAL = 8, PVGPU_FORMANT_CEPSTRAL = 9 };
 enum { PVGPU_NORMAL_PV = 0, PVGPU_PHASE_LOCKED = 1, PVGPU_INT_RATIO = 2 };
 
 /* sample formats of the batch entry points */
@@ -116,7 +121,7 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
 int pvgpu_batch_stats(const pvgpu_batch *b, int64_t *kernel_launches, int64_t *slices, int64_t *h2d_bytes, int64_t *d2h_bytes);
 int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);
 /* Per-kernel device timing with CUDA events recorded on the launching stream around every launch.  kinds:
- * 0 analyse, 1 phase core (polar), 2 synthesise, 3 overlap-add + resample, 4 fused synthesise + overlap-add + resample, 5 fixed phase (robotic/whisper on polar spectra),
+ * 0 analyse, 1 phase core (polar), 2 synthesise, 3 overlap-add + resample, 4 fused synthesise + overlap-add + resample, 5 fixed phase (robotic/whisper on polar spectra) or the cepstral envelope kernel (modes 8 / 9),
  * 6 lock_peaks, 7 lock_chain (phase-locked core on Cartesian spectra).
  * pvgpu_batch_kernel_times synchronises the device and returns the totals since profiling was enabled. */
 enum { PVGPU_KINDS = 8 };

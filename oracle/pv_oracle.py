@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libpv_oracle.so")
 REF_DIR = os.path.join(HERE, "_ref")
 REF_DRV = os.path.join(REF_DIR, "pvref_drv")
 REF_EXE = os.path.join(REF_DIR, "audiomod-exe")
+REF_DRV_CEP = os.path.join(REF_DIR, "pvref_drv_cep")   # the reference with its commented-out cepstral routine switched on
 
 # mode constants of the reference (include/dafx/phasevocoder.h:22-30)
 CONSTANT, NORMAL_SHIFT, GENDER_CHANGE, FORMANT_PRESERVE = -1, 0, 1, 2
@@ -190,15 +191,20 @@ def have_ref() -> bool:
     return os.path.exists(REF_DRV) and os.access(REF_DRV, os.X_OK)
 
 
+def have_ref_cepstral() -> bool:
+    return os.path.exists(REF_DRV_CEP) and os.access(REF_DRV_CEP, os.X_OK)
+
+
 def run_ref(x: np.ndarray, sr: int, timeratio: float = 1.0, semitones: float = 0.0, mode: int = NORMAL_SHIFT,
-            coremode: int = 1, fftsize: int = 2048, block: int = 0, protocol: str = "offline") -> np.ndarray:
-    """Run the unmodified reference library in its own OS process (fresh statics)."""
+            coremode: int = 1, fftsize: int = 2048, block: int = 0, protocol: str = "offline", cepstral: bool = False) -> np.ndarray:
+    """Run the unmodified reference library in its own OS process (fresh statics).  cepstral=True: the variant whose gender /
+    formant modes (1 / 2) call formantShiftSlice (oracle/Makefile, pvref_drv_cep)."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     ch = x.shape[0]
     with tempfile.TemporaryDirectory(prefix="pvref_") as d:
         fi, fo = os.path.join(d, "i.f32"), os.path.join(d, "o.f32")
         x.tofile(fi)
-        subprocess.check_call([REF_DRV, str(sr), str(ch), repr(float(timeratio)), repr(float(semitones)), str(mode),
+        subprocess.check_call([REF_DRV_CEP if cepstral else REF_DRV, str(sr), str(ch), repr(float(timeratio)), repr(float(semitones)), str(mode),
                                str(coremode), str(fftsize), fi, fo, str(block), protocol])
         y = np.fromfile(fo, dtype=np.float32)
     return y.reshape(ch, -1)
