@@ -47,6 +47,10 @@ WORKLOADS = {   # name: (sr, channels, timeratio, semitones, mode, coremode, fft
     "cfg5-vocoder-2048": (44100, 2, 1.0, 0.0, 3, 1, 2048, 1024),
     "cfg5-robotic-512": (44100, 2, 1.0, 0.0, 6, 1, 512, 1024),
     "cfg5-robotic-8192": (44100, 2, 1.0, 0.0, 6, 1, 8192, 1024),
+    # not BASELINE configurations: the optional cepstral gender mode, and FFT sizes outside 512..8192 (generic one-CTA-per-frame kernels)
+    "cepstral-gender": (44100, 1, 1.0, 4.0, 8, 1, 2048, 4096),
+    "generic-256": (44100, 1, 1.0, 7.0, 0, 1, 256, 1024),
+    "generic-16384": (48000, 1, 1.25, 0.0, 5, 1, 16384, 256),
 }
 METRIC = "audio-sec/sec, 2048-pt PV pitch-shift, batched streams"
 UNIT = "audio-s/s"
@@ -242,6 +246,11 @@ def reference_rows(rows_f32):
     """The unmodified reference (one fresh process per stream) on the given [channels, n] float32 streams; falls back to the
     C restatement (pinned bit-exactly to it by tests/test_oracle_vs_ref.py) when oracle/_ref was not shipped."""
     from oracle import pv_oracle as O
+    if MODE in (8, 9):   # the optional cepstral modes: checked against the reference built with formantShiftSlice switched on
+        if not O.have_ref_cepstral():
+            raise SystemExit("the cepstral workloads need oracle/_ref/pvref_drv_cep as their checker (use --no-parity)")
+        return [O.run_ref(x, SR, timeratio=TIMERATIO, semitones=SEMITONES, mode=MODE - 7, coremode=COREMODE, fftsize=FFT, cepstral=True)
+                for x in rows_f32], "reference"
     if O.have_ref():
         return [O.run_ref(x, SR, timeratio=TIMERATIO, semitones=SEMITONES, mode=MODE, coremode=COREMODE, fftsize=FFT) for x in rows_f32], "reference"
     return [O.run_offline(x, SR, timeratio=TIMERATIO, semitones=SEMITONES, mode=MODE, coremode=COREMODE, fftsize=FFT) for x in rows_f32], "port"
