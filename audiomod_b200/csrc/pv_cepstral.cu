@@ -20,6 +20,8 @@ namespace pvgpu {
 
 constexpr int kCepCutoff = 60;   // phasevocoderprocess.cc:946
 
+__device__ __forceinline__ float env_at_or_zero(const float *env, int src, int nc) { return src > nc ? 0.f : env[src]; }
+
 template <int N>
 __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_cepstral(const DevPlan p, const DevRows g, float env_comp, int nf, int total) {
     constexpr int NC = N / 2;
@@ -47,20 +49,33 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_cepstral(cons
     // ---- log-magnitude spectrum (imaginary parts 0) through the inverse real-FFT pre-pass (kiss_fftr.c:123-159) ----
     if (active) {
         const float2 *__restrict__ stw = p.stw_inv;
+        constexpr int U = Q >= 4 ? 4 : Q;   // pairs per step: their (up to 16) loads are all in flight before the first logf
 #pragma unroll 1
-        for (int q = 0; q < Q; ++q) {
-            const int kk = t + T * q;
-            const float fk = logf(mag_of(kk) + 0.000001f), fq = logf(mag_of(NC - kk) + 0.000001f);
-            if (kk == 0) {
-                buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk + fq, fk - fq);
-            } else {
-                const float2 fek = make_float2(__fadd_rn(fk, fq), 0.f), d = make_float2(__fsub_rn(fk, fq), 0.f);
-                const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
-                const float2 a = cadd_rn(fek, fok);
-                const float2 b = csub_rn(fek, fok);
-                buf[sa + fft_pad(fft_slot_of_input<NC>(T * q))] = a;
-                buf[sb + (t == 0 ? fft_pad(fft_slot_of_input<NC>((T * (16 - q)) & (NC - 1))) : fft_pad(fft_slot_of_input<NC>(T * (15 - q))))] =
-                    make_float2(b.x, -b.y);
+        for (int q0 = 0; q0 < Q; q0 += U) {
+            float la[U], lb[U], ha[U], hb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int kk = t + T * (q0 + u);
+                la[u] = ga[kk]; ha[u] = ga[NC - kk];
+                lb[u] = g.spec ? gb[kk] : 0.f; hb[u] = g.spec ? gb[NC - kk] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + u, kk = t + T * q;
+                const float ml = g.spec ? __fsqrt_rn(__fadd_rn(__fmul_rn(la[u], la[u]), __fmul_rn(lb[u], lb[u]))) : la[u];
+                const float mh = g.spec ? __fsqrt_rn(__fadd_rn(__fmul_rn(ha[u], ha[u]), __fmul_rn(hb[u], hb[u]))) : ha[u];
+                const float fk = logf(ml + 0.000001f), fq = logf(mh + 0.000001f);
+                if (kk == 0) {
+                    buf[fft_pad(fft_slot_of_input<NC>(0))] = make_float2(fk + fq, fk - fq);
+                } else {
+                    const float2 fek = make_float2(__fadd_rn(fk, fq), 0.f), d = make_float2(__fsub_rn(fk, fq), 0.f);
+                    const float2 fok = cmul_rn(d, __ldg(&stw[kk]));
+                    const float2 a = cadd_rn(fek, fok);
+                    const float2 b = csub_rn(fek, fok);
+                    buf[sa + fft_pad(fft_slot_of_input<NC>(T * q))] = a;
+                    buf[sb + (t == 0 ? fft_pad(fft_slot_of_input<NC>((T * (16 - q)) & (NC - 1))) : fft_pad(fft_slot_of_input<NC>(T * (15 - q))))] =
+                        make_float2(b.x, -b.y);
+                }
             }
         }
         if (t == 0) {   // kk == NC/2 pairs with itself; the second write wins (kiss_fftr.c:150-155)
@@ -140,21 +155,27 @@ __global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_cepstral(cons
     frame_sync<T>(group);
     if (!active) return;
     // ---- whiten by the envelope, put the warped envelope back (:969-994), in place ----
-    for (int i = t; i <= NC; i += T) {
-        float e_new;
-        if (env_comp > 1.0f) {
-            const int src = __float2int_rn(__fmul_rn((float)i, env_comp));
-            e_new = src > NC ? 0.f : env[src];
-        } else {
-            e_new = i < NC ? env[__float2int_rn(__fmul_rn((float)i, env_comp))] : env[NC];   // the descending loop leaves bin N/2 alone
+    constexpr int kBins = NC / T;   // 16 bins per thread, plus bin NC for thread 0
+#pragma unroll 1
+    for (int j0 = 0; j0 < kBins; j0 += 4) {
+        float a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int i = t + T * (j0 + u); a[u] = ga[i]; b[u] = g.spec ? gb[i] : 0.f; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = t + T * (j0 + u);
+            const float e_new = env_comp > 1.0f ? env_at_or_zero(env, __float2int_rn(__fmul_rn((float)i, env_comp)), NC)
+                                                 : env[__float2int_rn(__fmul_rn((float)i, env_comp))];
+            const float e_old = env[i];
+            ga[i] = __fmul_rn(__fdiv_rn(a[u], e_old), e_new);
+            if (g.spec) gb[i] = __fmul_rn(__fdiv_rn(b[u], e_old), e_new);
         }
-        const float e_old = env[i];
-        if (g.spec) {
-            ga[i] = __fmul_rn(__fdiv_rn(ga[i], e_old), e_new);
-            gb[i] = __fmul_rn(__fdiv_rn(gb[i], e_old), e_new);
-        } else {
-            ga[i] = __fmul_rn(__fdiv_rn(ga[i], e_old), e_new);
-        }
+    }
+    if (t == 0) {   // bin N/2: warped like the rest when compressing, left alone by the descending loop of the expanding direction
+        const float e_old = env[NC];
+        const float e_new = env_comp > 1.0f ? env_at_or_zero(env, __float2int_rn(__fmul_rn((float)NC, env_comp)), NC) : e_old;
+        ga[NC] = __fmul_rn(__fdiv_rn(ga[NC], e_old), e_new);
+        if (g.spec) gb[NC] = __fmul_rn(__fdiv_rn(gb[NC], e_old), e_new);
     }
 }
 
