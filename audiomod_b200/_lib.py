@@ -30,6 +30,13 @@ class Info(C.Structure):
                 ("resampler_den", C.c_uint32), ("outbuf_capacity", C.c_int64)]
 
 
+class Fx(C.Structure):
+    _fields_ = [("kind", C.c_int), ("p", C.c_float * 5)]
+
+
+FX_GAIN, FX_COMPRESSOR, FX_LIMITER = 1, 2, 3
+
+
 class WavJob(C.Structure):
     _fields_ = [("in_path", C.c_char_p), ("out_path", C.c_char_p), ("status", C.c_int), ("sample_rate", C.c_int), ("channels", C.c_int),
                 ("bits", C.c_int), ("frames_in", C.c_int64), ("frames_out", C.c_int64), ("message", C.c_char * 160)]
@@ -66,6 +73,7 @@ SYMBOLS = {
     "pvgpu_batch_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i64p]),
     "pvgpu_batch_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "pvgpu_batch_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
+    "pvgpu_batch_set_postchain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pvgpu_run_wav_files": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "pvgpu_mbatch_create": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int64, C.POINTER(C.c_int), C.c_int, _vpp]),
     "pvgpu_mbatch_destroy": (None, [C.c_void_p]),

@@ -135,6 +135,7 @@ struct Pipeline {
     // unless the schedule overlaps more frames / history slices than their per-CTA tables hold, then the fused kernel, which
     // has no such limit), 0 split only, 1 fused wherever the FFT size has one.  PVGPU_FUSED=0/1 overrides for every instance.
     int fused_pref = -1;
+    PostChain post{};           // FFT-free effects applied to the output columns a chunk completes (pv_post.cu); n == 0: none
     FusedArgs fa{};             // run / ring / window shape; per-launch fields are filled in run_synth_ola
     // host copy of the uploaded records + the resampler work lists built from them (ResampleRun, pv_kernels.cuh)
     std::vector<SliceRec> h_recs;
@@ -569,6 +570,7 @@ struct Workspace {
     DevBuf mag, phase, frames, prev_phase, prev_out, peaks, first, n_in, n_out;
     DevBuf lock_hdr, lock_rec, lock_map, lock_csn, lock_tail, lock_kind, lock_rot;   // phase-locked core on Cartesian spectra
     DevBuf ola_tail, res_hist;                                                       // fused kernel: per-row carry between launches
+    DevBuf post_state;                                                               // post-chain: per-row effect state
     size_t lock_slots = 0;     // (row, frame) slots per lock buffer set; nbuf sets are allocated when the fused pipeline overlaps stages
     int rows = 0, F = 0, Fr = 0;
 
@@ -590,6 +592,7 @@ struct Workspace {
             CU(ola_tail.ensure(sizeof(float) * (size_t)rows * p.N));
             CU(res_hist.ensure(sizeof(float) * (size_t)rows * std::max(pl.fa.hist_len, 1)));
         }
+        if (pl.post.n > 0) CU(post_state.ensure(sizeof(float) * (size_t)rows * postchain_state_stride(pl.post)));
         CU(prev_phase.ensure(sizeof(float) * (size_t)rows * p.half));
         CU(prev_out.ensure(sizeof(float) * (size_t)rows * p.half));
         CU(peaks.ensure(sizeof(int) * (size_t)streams * (1 + pl.max_peaks())));
@@ -622,6 +625,7 @@ struct Workspace {
             CU(cudaMemsetAsync(lock_kind.p, 0, sizeof(int) * (size_t)rows, st));
             CU(cudaMemsetAsync(lock_rot.p, 0, sizeof(float) * (size_t)rows * pl.max_peaks(), st));
         }
+        if (pl.post.n > 0) launch_postchain_reset(pl.post, post_state.as<float>(), rows, st);
         if (pl.fused) {   // empty accumulator, zero history (speex mem is zero-initialised)
             CU(cudaMemsetAsync(ola_tail.p, 0, sizeof(float) * (size_t)rows * p.N, st));
             CU(cudaMemsetAsync(res_hist.p, 0, sizeof(float) * (size_t)rows * std::max(pl.fa.hist_len, 1), st));
@@ -805,6 +809,11 @@ static int run_chunks(pvgpu_batch *b, pvgpu_batch::Ctx &ctx, DevRows g, bool ove
         }
         if (pl.fused) { if ((rc = pl.run_synth_ola(g, k0, nf, sc))) return rc; }
         else pl.run_ola(g, k0, nf, sc);
+        if (pl.post.n > 0) {   // the output columns this chunk completed go through the effect chain before anything reads them
+            const SliceRec &first = pl.h_recs[k0 - pl.recs_base], &last = pl.h_recs[k0 + nf - 1 - pl.recs_base];
+            launch_postchain(g, pl.post, ctx.ws.post_state.as<float>(), first.out_off, last.out_off + ((last.flags & 1) ? 0 : last.n_write), sc);
+            ++pl.launches;
+        }
         if (overlap) CU(cudaEventRecord(ctx.ev_ola[e], sc));
         if ((rc = after(ci, k0, nf, sc))) return rc;
     }
@@ -918,6 +927,38 @@ int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, i
     if (frames_per_chunk > 0 && frames_per_chunk != b->frames_per_chunk) { b->frames_per_chunk = frames_per_chunk; b->run_for_chunk = 0; }
     if (rows_per_group > 0) { b->rows_per_group = rows_per_group; b->time_sliced = false; }   // explicit row groups pipeline across rows instead of time
     if (contexts > 0) b->n_contexts = std::min(contexts, (int)pvgpu_batch::kCtx);
+    return PVGPU_OK;
+}
+
+int pvgpu_batch_set_postchain(pvgpu_batch *b, const pvgpu_fx *chain, int n_fx) {
+    if (!b || n_fx < 0 || n_fx > kMaxPostFx || (n_fx > 0 && !chain)) return fail(PVGPU_EINVAL, "bad post-chain (at most %d effects)", kMaxPostFx);
+    PostChain pc{};
+    const int sr = b->cfg.sample_rate;
+    for (int i = 0; i < n_fx; ++i) {
+        const pvgpu_fx &f = chain[i];
+        PostFx &o = pc.fx[i];
+        o.kind = f.kind;
+        if (f.kind == PVGPU_FX_GAIN) {                    // gain::gain, src/gain/gain.cc:21-25
+            o.p[0] = f.p[0];
+        } else if (f.kind == PVGPU_FX_COMPRESSOR) {       // compressor::compressor, src/dynamics/compressor.cc:16-42
+            const float tau_a = f.p[3], tau_r = f.p[4];
+            o.p[0] = f.p[0]; o.p[1] = f.p[1]; o.p[2] = f.p[2];
+            o.p[3] = (float)std::exp(-1 / (0.001 * sr * tau_a));
+            o.p[4] = (float)std::exp(-1 / (0.001 * sr * tau_r));
+            if (!(f.p[1] > 0.f)) return fail(PVGPU_EINVAL, "compressor ratio must be positive");
+        } else if (f.kind == PVGPU_FX_LIMITER) {          // limiter::limiter, src/dynamics/limiter.cc:16-39 (LIMIT_OFFSET 0.01, ahead 6 ms)
+            o.p[0] = (float)std::pow(10.0, f.p[1] / 20.0);
+            o.p[1] = (float)std::pow(10.0, (f.p[0] - 0.01) / 20.0);
+            o.p[2] = (float)std::exp(-1.0 / (sr * 0.001 * f.p[2]));
+            o.p[3] = (float)std::exp(-1.0 / (sr * 0.001 * f.p[3]));
+            o.p[4] = (float)std::pow(10.0, -120.0 / 20.0);
+            o.delay = (int)(sr * 0.001 * 6.0f) + 1;
+        } else {
+            return fail(PVGPU_EINVAL, "unknown effect kind %d", f.kind);
+        }
+    }
+    pc.n = n_fx;
+    b->pl.post = pc;
     return PVGPU_OK;
 }
 
@@ -1046,6 +1087,7 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
     if (!b || !d_in || !d_out) return fail(PVGPU_EINVAL, "null argument");
     if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
     if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
+    if (fmt != PVGPU_F32 && b->pl.post.n > 0) return fail(PVGPU_EINVAL, "the post-chain works on float32 rows");
     CU(cudaSetDevice(b->pl.device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy;
     b->last_stream = st;
@@ -1204,6 +1246,7 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
     if (!b || !in_rows || !out_rows) return fail(PVGPU_EINVAL, "null argument");
     if (!b->planned) return fail(PVGPU_ESTATE, "pvgpu_batch_plan has not been called");
     if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
+    if (fmt != PVGPU_F32 && b->pl.post.n > 0) return fail(PVGPU_EINVAL, "the post-chain works on float32 rows");
     CU(cudaSetDevice(b->pl.device));
     return drain_after_error(b, batch_run_host_impl(b, in_rows, out_rows, fmt));
 }

@@ -137,6 +137,18 @@ cudaError_t launch_synth_ola(const DevPlan &p, const DevRows &g, const FusedArgs
 
 // cepstral spectral-envelope modification of the chunk's spectra in place (pv_cepstral.cu); false: no kernel for this FFT size
 bool launch_cepstral(const DevPlan &p, const DevRows &g, float env_comp, int nframes, cudaStream_t st);
+// ---- post-chain of FFT-free effects on the output rows (pv_post.cu) ----
+constexpr int kMaxPostFx = 4;
+enum { kFxGain = 1, kFxCompressor = 2, kFxLimiter = 3 };
+// coefficients as the reference's constructors compute them (host, glibc): gain p[0]; compressor p = {threshold dB, ratio,
+// make-up dB, alphaAttack, alphaRelease}; limiter p = {makeUpGain, threshold (linear), alphaAttack, alphaRelease, initial xPeak},
+// delay = (int)(sr * 0.001 * 6) + 1 samples of look-ahead
+struct PostFx { int kind; int delay; float p[5]; };
+struct PostChain { int n; PostFx fx[kMaxPostFx]; };
+int postchain_state_stride(const PostChain &pc);
+void launch_postchain_reset(const PostChain &pc, float *state, int rows, cudaStream_t st);
+void launch_postchain(const DevRows &g, const PostChain &pc, float *state, int64_t col0, int64_t col1, cudaStream_t st);
+
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
 

@@ -182,6 +182,18 @@ class PhaseVocoderBatch:
         self.run_host_rows(in_rows, out_rows, fmt)
         return outs
 
+    def set_postchain(self, chain):
+        """FFT-free effects applied to the float32 output rows, in order (pvgpu_batch_set_postchain): a list of
+        ("gain", g), ("compressor", dBThreshold, ratio, dBMakeUpGain, attackMs, releaseMs), ("limiter", dBThreshold, dBMakeUpGain,
+        attackMs, releaseMs) -- the reference objects' constructor arguments.  An empty list clears the chain."""
+        kinds = {"gain": _lib.FX_GAIN, "compressor": _lib.FX_COMPRESSOR, "limiter": _lib.FX_LIMITER}
+        arr = (_lib.Fx * max(len(chain), 1))()
+        for i, fx in enumerate(chain):
+            arr[i].kind = kinds[fx[0]]
+            for j, v in enumerate(fx[1:]):
+                arr[i].p[j] = float(v)
+        check(_lib.lib().pvgpu_batch_set_postchain(self._h, arr, len(chain)))
+
     def set_fused(self, enable=True):
         """True: the fused inverse-FFT + overlap-add + resampler kernel; False: the split kernels; None: automatic (split unless the
         stretch ratio exceeds their table limits).  Bit-identical results either way."""

@@ -117,6 +117,16 @@ int pvgpu_batch_synchronize(pvgpu_batch *b);
 /* Host buffers (pinned or pageable): one pointer per row; copies in, runs, copies out, synchronises.
  * Stream groups are pipelined so H2D, kernels and D2H overlap. */
 int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const *out_rows, int fmt);
+/* FFT-free effects as a post-chain on the batch's float32 output rows: applied, in order, to the columns
+ * every frame chunk completes, with their state carried along the row -- exactly the reference objects' processBlock run over a
+ * stream's whole output, whatever the block size.  kinds and parameters (the reference constructors' arguments):
+ *   PVGPU_FX_GAIN        p = {gain}                                                          src/gain/gain.cc
+ *   PVGPU_FX_COMPRESSOR  p = {dBThreshold, ratio, dBMakeUpGain, attackTimeMs, releaseTimeMs}  src/dynamics/compressor.cc
+ *   PVGPU_FX_LIMITER     p = {dBThreshold, dBMakeUpGain, attackTimeMs, releaseTimeMs}          src/dynamics/limiter.cc (6 ms look-ahead)
+ * n_fx = 0 clears the chain; at most 4 effects.  Takes effect at the next run. */
+enum { PVGPU_FX_GAIN = 1, PVGPU_FX_COMPRESSOR = 2, PVGPU_FX_LIMITER = 3 };
+typedef struct pvgpu_fx { int kind; float p[5]; } pvgpu_fx;
+int pvgpu_batch_set_postchain(pvgpu_batch *b, const pvgpu_fx *chain, int n_fx);
 /* counters of the last run: kernels launched, slices per stream, H2D/D2H bytes */
 int pvgpu_batch_stats(const pvgpu_batch *b, int64_t *kernel_launches, int64_t *slices, int64_t *h2d_bytes, int64_t *d2h_bytes);
 int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);

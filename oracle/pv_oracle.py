@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, "libpv_oracle.so")
 REF_DIR = os.path.join(HERE, "_ref")
 REF_DRV = os.path.join(REF_DIR, "pvref_drv")
 REF_EXE = os.path.join(REF_DIR, "audiomod-exe")
+REF_FX = os.path.join(REF_DIR, "fxref_drv")             # the reference's gain / compressor / limiter objects over a float32 file
 REF_DRV_CEP = os.path.join(REF_DIR, "pvref_drv_cep")   # the reference with its commented-out cepstral routine switched on
 
 # mode constants of the reference (include/dafx/phasevocoder.h:22-30)
@@ -206,5 +207,25 @@ def run_ref(x: np.ndarray, sr: int, timeratio: float = 1.0, semitones: float = 0
         x.tofile(fi)
         subprocess.check_call([REF_DRV_CEP if cepstral else REF_DRV, str(sr), str(ch), repr(float(timeratio)), repr(float(semitones)), str(mode),
                                str(coremode), str(fftsize), fi, fo, str(block), protocol])
+        y = np.fromfile(fo, dtype=np.float32)
+    return y.reshape(ch, -1)
+
+
+def have_ref_fx() -> bool:
+    return os.path.exists(REF_FX) and os.access(REF_FX, os.X_OK)
+
+
+def run_ref_fx(x: np.ndarray, sr: int, chain) -> np.ndarray:
+    """chain: list of ("gain", g) / ("compressor", thr, ratio, makeup, att, rel) / ("limiter", thr, makeup, att, rel), applied in
+    order by the unmodified reference's objects (blocks of 480 samples, in place)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    ch = x.shape[0]
+    args = []
+    for fx in chain:
+        args += [fx[0]] + [repr(float(v)) for v in fx[1:]]
+    with tempfile.TemporaryDirectory(prefix="fxref_") as d:
+        fi, fo = os.path.join(d, "i.f32"), os.path.join(d, "o.f32")
+        x.tofile(fi)
+        subprocess.check_call([REF_FX, str(sr), str(ch), fi, fo] + args)
         y = np.fromfile(fo, dtype=np.float32)
     return y.reshape(ch, -1)
