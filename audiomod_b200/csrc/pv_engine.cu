@@ -201,6 +201,11 @@ struct Pipeline {
         p.rs_num = d.rs.num; p.rs_den = d.rs.den; p.rs_filt_len = d.rs.filt_len; p.rs_oversample = d.rs.oversample;
         p.rs_int_adv = d.rs.int_adv; p.rs_frac_adv = d.rs.frac_adv;
         p.rs_table_len = (int)d.rs.table.size();
+        if (!(d.robotic || d.whisper || d.vocoder || d.constant_mode) && d.cfg.coremode != 2 &&
+            !(d.cfg.coremode == 1 && lock_smem_bytes(p, d.cfg.channels, max_peaks()) <= (size_t)200 * 1024) &&
+            smem_phase_core(p, d.cfg.channels, max_peaks()) + 64 > (size_t)200 * 1024)
+            return fail(PVGPU_EINVAL, "%d channels at FFT size %d need more shared memory per stream than the device has (the phase core keeps every channel's phase state on chip)",
+                        d.cfg.channels, d.N);
         int rc;
         if ((rc = upload(b_window, t.window.data(), sizeof(float) * t.window.size()))) return rc;
         if ((rc = upload(b_twf, t.tw_fwd.data(), sizeof(float) * t.tw_fwd.size()))) return rc;
