@@ -108,6 +108,26 @@ def test_no_gpu_fails_loudly(pvlib):
     with pytest.raises(A.PvgpuError) as e:
         A.PhaseVocoderBatch(4, 1000, 44100, 1, 1.0, 7.0)
     assert e.value.code == _lib.ECUDA
+    with pytest.raises(A.PvgpuError) as e:
+        A.PhaseVocoderMultiBatch(4, 1000, 44100, 1, 1.0, 7.0)
+    assert e.value.code == _lib.ECUDA
+    with pytest.raises(A.PvgpuError) as e:
+        A.run_wav_files([("/nonexistent/in.wav", "/nonexistent/out.wav")], 1.0, 7.0)
+    assert e.value.code == _lib.ECUDA
+    with pytest.raises(A.PvgpuError) as e:
+        A.HostBuffer(1 << 20, 0)
+    assert e.value.code == _lib.ECUDA
+
+
+def test_extension_modes_derive_like_their_parity_twins(pvlib):
+    """Modes 8 / 9 (cepstral gender / formant) share every size, hop and resampler setting with modes 1 / 2; they only swap the
+    spectral-envelope routine.  Unknown modes stay invalid."""
+    import audiomod_b200 as A
+    for st in (4.0, -4.0, 7.0):
+        for twin, ext in ((A.GENDER_CHANGE, A.GENDER_CEPSTRAL), (A.FORMANT_PRESERVE, A.FORMANT_CEPSTRAL)):
+            assert A.describe(44100, 1, 1.0, st, twin, 1, 2048) == A.describe(44100, 1, 1.0, st, ext, 1, 2048)
+            assert A.plan_counts(44100, 44100, 1, 1.0, st, twin, 1, 2048) == A.plan_counts(44100, 44100, 1, 1.0, st, ext, 1, 2048)
+    assert A.plan_counts(44100, 44100, 1, 1.0, 4.0, 10, 1, 2048)["n_out"] == 0
 
 
 def test_product_does_not_import_oracle():
