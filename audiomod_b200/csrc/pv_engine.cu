@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <map>
 #include <memory>
 #include <new>
@@ -39,6 +40,16 @@ int fail(int code, const char *fmt, ...) {
     va_end(ap);
     g_err = buf;
     return code;
+}
+// No exception may cross the C ABI (std::vector / std::map growth can throw): entry points run their bodies through this.
+template <class F> static int guarded(F f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return fail(PVGPU_ENOMEM, "out of host memory");
+    } catch (const std::exception &e) {
+        return fail(PVGPU_ESTATE, "unexpected failure: %s", e.what());
+    }
 }
 #define CU(call)                                                                                      \
     do {                                                                                              \
@@ -884,7 +895,11 @@ int pvgpu_plan_counts(const pvgpu_config *cfg, int64_t n_in, int block, int64_t 
     return PVGPU_OK;
 }
 
+static int pvgpu_batch_create_body(const pvgpu_config *cfg, int n_streams, int64_t max_in_samples, pvgpu_batch **out);
 int pvgpu_batch_create(const pvgpu_config *cfg, int n_streams, int64_t max_in_samples, pvgpu_batch **out) {
+    return guarded([&]() -> int { return pvgpu_batch_create_body(cfg, n_streams, max_in_samples, out); });
+}
+static int pvgpu_batch_create_body(const pvgpu_config *cfg, int n_streams, int64_t max_in_samples, pvgpu_batch **out) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!out || n_streams < 1 || max_in_samples < 0) return fail(PVGPU_EINVAL, "bad batch arguments");
@@ -974,7 +989,11 @@ int pvgpu_batch_set_fused(pvgpu_batch *b, int enable) {
     return PVGPU_OK;
 }
 
+static int pvgpu_batch_plan_body(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_out);
 int pvgpu_batch_plan(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_out) {
+    return guarded([&]() -> int { return pvgpu_batch_plan_body(b, n_in, block, n_out); });
+}
+static int pvgpu_batch_plan_body(pvgpu_batch *b, const int64_t *n_in, int block, int64_t *n_out) {
     if (!b || !n_in) return fail(PVGPU_EINVAL, "null argument");
     CU(cudaSetDevice(b->pl.device));
     Pipeline &pl = b->pl;
@@ -1096,7 +1115,7 @@ int pvgpu_batch_run_device(pvgpu_batch *b, const void *d_in, int64_t in_stride, 
     CU(cudaSetDevice(b->pl.device));
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy;
     b->last_stream = st;
-    return drain_after_error(b, batch_run_device_impl(b, d_in, in_stride, d_out, out_stride, fmt, st));
+    return drain_after_error(b, guarded([&]() -> int { return batch_run_device_impl(b, d_in, in_stride, d_out, out_stride, fmt, st); }));
 }
 
 int pvgpu_batch_synchronize(pvgpu_batch *b) {
@@ -1253,7 +1272,7 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
     if (fmt != PVGPU_F32 && fmt != PVGPU_S16) return fail(PVGPU_EINVAL, "unknown sample format %d", fmt);
     if (fmt != PVGPU_F32 && b->pl.post.n > 0) return fail(PVGPU_EINVAL, "the post-chain works on float32 rows");
     CU(cudaSetDevice(b->pl.device));
-    return drain_after_error(b, batch_run_host_impl(b, in_rows, out_rows, fmt));
+    return drain_after_error(b, guarded([&]() -> int { return batch_run_host_impl(b, in_rows, out_rows, fmt); }));
 }
 
 int pvgpu_batch_profile(pvgpu_batch *b, int enable) {
@@ -1504,7 +1523,11 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
 
 extern "C" {
 
+static int pvgpu_create_body(const pvgpu_config *cfg, pvgpu_stream **out);
 int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out) {
+    return guarded([&]() -> int { return pvgpu_create_body(cfg, out); });
+}
+static int pvgpu_create_body(const pvgpu_config *cfg, pvgpu_stream **out) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!out) return fail(PVGPU_EINVAL, "null out pointer");
@@ -1550,7 +1573,11 @@ int pvgpu_stream_info(const pvgpu_stream *s, pvgpu_info *info) {
     return PVGPU_OK;
 }
 
+static int pvgpu_process_body(pvgpu_stream *s, const float *const *in, int n);
 int pvgpu_process(pvgpu_stream *s, const float *const *in, int n) {
+    return guarded([&]() -> int { return pvgpu_process_body(s, in, n); });
+}
+static int pvgpu_process_body(pvgpu_stream *s, const float *const *in, int n) {
     if (!s || n < 0 || (n > 0 && !in)) return fail(PVGPU_EINVAL, "bad argument");
     if (!s->pl.d.valid_mode) { s->num_res = 0; return PVGPU_OK; }  // phasevocoder.cc:104-106: unknown mode does nothing
     const int C = s->cfg.channels;

@@ -119,8 +119,14 @@ template <class Fn> static int for_each_device(pvgpu_mbatch *m, Fn fn) {
     for (int d = 0; d < nd; ++d)
         th.emplace_back([&, d]() {
             bind_thread_to_device_node(m->devices[d]);
-            rc[d] = fn(d);
-            if (rc[d] != PVGPU_OK) msg[d] = last_error_string();
+            try {   // an exception must neither leave the thread nor cross the C ABI
+                rc[d] = fn(d);
+                if (rc[d] != PVGPU_OK) msg[d] = last_error_string();
+            } catch (const std::bad_alloc &) {
+                rc[d] = PVGPU_ENOMEM; msg[d] = "out of host memory";
+            } catch (...) {
+                rc[d] = PVGPU_ESTATE; msg[d] = "unexpected failure";
+            }
         });
     for (auto &t : th) t.join();
     for (int d = 0; d < nd; ++d)

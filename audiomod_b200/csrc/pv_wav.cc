@@ -15,7 +15,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <map>
+#include <new>
 #include <string>
 #include <thread>
 #include <tuple>
@@ -126,7 +128,19 @@ static std::string write_wav16(const char *path, int sample_rate, int channels, 
 
 using namespace pvgpu;
 
+static int run_wav_files_impl(const pvgpu_config *cfg, pvgpu_wav_job *jobs, int n_jobs, const int *devices, int n_dev);
+
 extern "C" int pvgpu_run_wav_files(const pvgpu_config *cfg, pvgpu_wav_job *jobs, int n_jobs, const int *devices, int n_dev) {
+    try {   // no exception may cross the C ABI (the reference aborts on allocation failure, memallocators.h:91; here: an error code)
+        return run_wav_files_impl(cfg, jobs, n_jobs, devices, n_dev);
+    } catch (const std::bad_alloc &) {
+        return fail(PVGPU_ENOMEM, "out of host memory while reading the WAV files");
+    } catch (const std::exception &e) {
+        return fail(PVGPU_ESTATE, "unexpected failure: %s", e.what());
+    }
+}
+
+static int run_wav_files_impl(const pvgpu_config *cfg, pvgpu_wav_job *jobs, int n_jobs, const int *devices, int n_dev) {
     if (!cfg || !jobs || n_jobs < 0) return fail(PVGPU_EINVAL, "bad argument");
     if (pvgpu_device_count() < 1) return fail(PVGPU_ECUDA, "no CUDA device: the phase vocoder has no CPU fallback");
     std::vector<Job> js((size_t)n_jobs);
