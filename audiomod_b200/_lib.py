@@ -31,10 +31,10 @@ class Info(C.Structure):
 
 
 class Fx(C.Structure):
-    _fields_ = [("kind", C.c_int), ("p", C.c_float * 5)]
+    _fields_ = [("kind", C.c_int), ("p", C.c_float * 6)]
 
 
-FX_GAIN, FX_COMPRESSOR, FX_LIMITER = 1, 2, 3
+FX_GAIN, FX_COMPRESSOR, FX_LIMITER, FX_BIQUAD = 1, 2, 3, 4
 
 
 class WavJob(C.Structure):
@@ -74,6 +74,8 @@ SYMBOLS = {
     "pvgpu_batch_tune": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "pvgpu_batch_set_fused": (C.c_int, [C.c_void_p, C.c_int]),
     "pvgpu_batch_set_postchain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "pvgpu_equalizer_chain": (C.c_int, [_fp, C.c_void_p, C.POINTER(C.c_int)]),
+    "pvgpu_biquad_design": (C.c_int, [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _fp]),
     "pvgpu_run_wav_files": (C.c_int, [C.POINTER(Config), C.c_void_p, C.c_int, C.POINTER(C.c_int), C.c_int]),
     "pvgpu_mbatch_create": (C.c_int, [C.POINTER(Config), C.c_int, C.c_int64, C.POINTER(C.c_int), C.c_int, _vpp]),
     "pvgpu_mbatch_destroy": (None, [C.c_void_p]),

@@ -950,6 +950,57 @@ int pvgpu_batch_tune(pvgpu_batch *b, int frames_per_chunk, int rows_per_group, i
     return PVGPU_OK;
 }
 
+// biquadfilter::computeCoeffs (src/common/filters/biquadfilter.cc:113-195: the RBJ audio-EQ-cookbook sections), with the
+// reference's mix of float members and double libm calls; coeffs = {b0, b1, b2, a0, a1, a2} as it stores them (floats).
+int pvgpu_biquad_design(int type, int sample_rate, float cutoff, float q, float db_gain, float *coeffs) {
+    if (!coeffs || sample_rate <= 0 || !(q > 0.f) || type < 0 || type > 8) return fail(PVGPU_EINVAL, "bad biquad parameters");
+    const float a = (float)std::pow(10.0, db_gain / 40.0);
+    const float omega = (float)(2 * M_PI * cutoff / sample_rate);
+    const float alpha = (float)(std::sin((double)omega) / 2.0 / q);
+    const double cw = std::cos((double)omega), sw = std::sin((double)omega), sa = std::sqrt((double)a);
+    float b0, b1, b2, a0, a1, a2;
+    switch (type) {
+        case 5:  b0 = b2 = (float)((1.0 - cw) / 2.0); b1 = (float)(1.0 - cw); a0 = (float)(1.0 + alpha); a1 = (float)(-2.0 * cw); a2 = 1 - alpha; break;   // lowPass
+        case 0:  b0 = b2 = (float)((1.0 + cw) / 2.0); b1 = (float)(-(1.0 + cw)); a0 = (float)(1.0 + alpha); a1 = (float)(-2.0 * cw); a2 = 1 - alpha; break;  // highPass
+        case 6:  b0 = (float)(sw / 2); b1 = 0; b2 = (float)(-sw / 2); a0 = 1 + alpha; a1 = (float)(-2 * cw); a2 = 1 - alpha; break;                            // bandpass, constant skirt
+        case 7:  b0 = alpha; b1 = 0; b2 = -alpha; a0 = 1 + alpha; a1 = (float)(-2 * cw); a2 = 1 - alpha; break;                                                 // bandpass, constant 0 dB peak
+        case 3:  b0 = 1; b1 = (float)(-2 * cw); b2 = 1; a0 = 1 + alpha; a1 = (float)(-2 * cw); a2 = 1 - alpha; break;                                           // notch
+        case 8:  b0 = 1 - alpha; b1 = (float)(-2 * cw); b2 = 1 + alpha; a0 = 1 + alpha; a1 = (float)(-2 * cw); a2 = 1 - alpha; break;                           // allpass
+        case 2:  b0 = 1 + alpha * a; b1 = (float)(-2 * cw); b2 = 1 - alpha * a; a0 = 1 + alpha / a; a1 = (float)(-2 * cw); a2 = 1 - alpha / a; break;           // peaking
+        case 1:                                                                                                                                              // lowShelf
+            b0 = (float)(a * (a + 1 - (a - 1) * cw + 2 * sa * alpha)); b1 = (float)(2 * a * (a - 1 - (a + 1) * cw)); b2 = (float)(a * (a + 1 - (a - 1) * cw - 2 * sa * alpha));
+            a0 = (float)(a + 1 + (a - 1) * cw + 2 * sa * alpha); a1 = (float)(-2 * (a - 1 + (a + 1) * cw)); a2 = (float)(a + 1 + (a - 1) * cw - 2 * sa * alpha);
+            break;
+        default:                                                                                                                                             // highShelf (4)
+            b0 = (float)(a * (a + 1 + (a - 1) * cw + 2 * sa * alpha)); b1 = (float)(-2 * a * (a - 1 + (a + 1) * cw)); b2 = (float)(a * (a + 1 + (a - 1) * cw - 2 * sa * alpha));
+            a0 = (float)(a + 1 - (a - 1) * cw + 2 * sa * alpha); a1 = (float)(2 * (a - 1 - (a + 1) * cw)); a2 = (float)(a + 1 - (a - 1) * cw - 2 * sa * alpha);
+            break;
+    }
+    coeffs[0] = b0; coeffs[1] = b1; coeffs[2] = b2; coeffs[3] = a0; coeffs[4] = a1; coeffs[5] = a2;
+    return PVGPU_OK;
+}
+
+// equalizer::equalizer + processBlock (src/equalizer/equalizer.cc:19-146, 613-647): eight biquad sections in a fixed order
+// (high-pass, low shelf, four peaking, high shelf, low-pass), each with {use flag, cutoff, Q, gain}; paramlist == NULL gives
+// the reference's defaults (only the 200 Hz high-pass is on).  Writes the enabled sections as PVGPU_FX_BIQUAD entries.
+int pvgpu_equalizer_chain(const float *paramlist, pvgpu_fx *chain, int *n_fx) {
+    if (!chain || !n_fx) return fail(PVGPU_EINVAL, "null argument");
+    static const float defaults[32] = {1, 200, 0.3f, 1.0f,  0, 400, 0.3f, -1.5f,  0, 1000, 0.3f, 1.5f,  0, 2000, 0.3f, 1.5f,
+                                       0, 3000, 0.3f, 1.5f,  0, 4000, 0.3f, 1.5f,  0, 5000, 0.3f, -1.5f,  0, 6000, 0.3f, 1.0f};
+    static const int types[8] = {0, 1, 2, 2, 2, 2, 4, 5};
+    const float *pl = paramlist ? paramlist : defaults;
+    int n = 0;
+    for (int b = 0; b < 8; ++b) {
+        if (!(pl[4 * b] > 0)) continue;
+        chain[n].kind = PVGPU_FX_BIQUAD;
+        chain[n].p[0] = (float)types[b]; chain[n].p[1] = pl[4 * b + 1]; chain[n].p[2] = pl[4 * b + 2]; chain[n].p[3] = pl[4 * b + 3];
+        chain[n].p[4] = chain[n].p[5] = 0.f;
+        ++n;
+    }
+    *n_fx = n;
+    return PVGPU_OK;
+}
+
 int pvgpu_batch_set_postchain(pvgpu_batch *b, const pvgpu_fx *chain, int n_fx) {
     if (!b || n_fx < 0 || n_fx > kMaxPostFx || (n_fx > 0 && !chain)) return fail(PVGPU_EINVAL, "bad post-chain (at most %d effects)", kMaxPostFx);
     PostChain pc{};
@@ -973,6 +1024,10 @@ int pvgpu_batch_set_postchain(pvgpu_batch *b, const pvgpu_fx *chain, int n_fx) {
             o.p[3] = (float)std::exp(-1.0 / (sr * 0.001 * f.p[3]));
             o.p[4] = (float)std::pow(10.0, -120.0 / 20.0);
             o.delay = (int)(sr * 0.001 * 6.0f) + 1;
+        } else if (f.kind == PVGPU_FX_BIQUAD) {           // biquadfilter::biquadfilter + computeCoeffs, src/common/filters/biquadfilter.cc:29-41,113-195
+            float c[6];
+            if (pvgpu_biquad_design((int)f.p[0], sr, f.p[1], f.p[2], f.p[3], c) != PVGPU_OK) return PVGPU_EINVAL;
+            for (int j = 0; j < 6; ++j) o.p[j] = c[j];
         } else {
             return fail(PVGPU_EINVAL, "unknown effect kind %d", f.kind);
         }

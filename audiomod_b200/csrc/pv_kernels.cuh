@@ -138,12 +138,12 @@ cudaError_t launch_synth_ola(const DevPlan &p, const DevRows &g, const FusedArgs
 // cepstral spectral-envelope modification of the chunk's spectra in place (pv_cepstral.cu); false: no kernel for this FFT size
 bool launch_cepstral(const DevPlan &p, const DevRows &g, float env_comp, int nframes, cudaStream_t st);
 // ---- post-chain of FFT-free effects on the output rows (pv_post.cu) ----
-constexpr int kMaxPostFx = 4;
-enum { kFxGain = 1, kFxCompressor = 2, kFxLimiter = 3 };
+constexpr int kMaxPostFx = 12;
+enum { kFxGain = 1, kFxCompressor = 2, kFxLimiter = 3, kFxBiquad = 4 };
 // coefficients as the reference's constructors compute them (host, glibc): gain p[0]; compressor p = {threshold dB, ratio,
 // make-up dB, alphaAttack, alphaRelease}; limiter p = {makeUpGain, threshold (linear), alphaAttack, alphaRelease, initial xPeak},
-// delay = (int)(sr * 0.001 * 6) + 1 samples of look-ahead
-struct PostFx { int kind; int delay; float p[5]; };
+// delay = (int)(sr * 0.001 * 6) + 1 samples of look-ahead; biquad p = {b0, b1, b2, a0, a1, a2} (biquadfilter::computeCoeffs)
+struct PostFx { int kind; int delay; float p[6]; };
 struct PostChain { int n; PostFx fx[kMaxPostFx]; };
 int postchain_state_stride(const PostChain &pc);
 void launch_postchain_reset(const PostChain &pc, float *state, int rows, cudaStream_t st);

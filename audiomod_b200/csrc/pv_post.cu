@@ -1,5 +1,7 @@
 // FFT-free effects as a post-chain on the batch's output rows: gain (src/gain/gain.cc:27-36),
-// compressor (src/dynamics/compressor.cc:54-77) and limiter (src/dynamics/limiter.cc:45-64) -- the per-sample recursions of
+// compressor (src/dynamics/compressor.cc:54-77), limiter (src/dynamics/limiter.cc:45-64) and biquad sections
+// (src/common/filters/biquadfilter.cc:53-60; eight of them in a fixed order are the equalizer, src/equalizer/equalizer.cc:613-647)
+// -- the per-sample recursions of
 // the reference's processBlock, run over the whole output stream of a row (they carry their state from block to block, so
 // the block size is invisible).  The recursions are serial in time (the attack / release coefficient of a sample depends
 // on the previous state), so the parallelism is across rows: one thread per row, a warp takes 32 rows and moves 32 x 32
@@ -10,7 +12,20 @@
 
 namespace pvgpu {
 
-struct FxRegs { float a, b; int pos; };   // compressor: a = dbyL_prev; limiter: a = xPeak, b = gain, pos = delay-line position
+// compressor: a = dbyL_prev; limiter: a = xPeak, b = gain, pos = delay-line position; biquad: a, b, c, d = x1, x2, y1, y2
+struct FxRegs { float a, b, c, d; int pos; };
+
+// biquadfilter::process (src/common/filters/biquadfilter.cc:53-60): direct form I, every product and sum rounded to float
+__device__ __forceinline__ float fx_biquad(float x, const PostFx &f, FxRegs &s) {
+    float acc = __fmul_rn(f.p[0], x);
+    acc = __fadd_rn(acc, __fmul_rn(f.p[1], s.a));
+    acc = __fadd_rn(acc, __fmul_rn(f.p[2], s.b));
+    acc = __fsub_rn(acc, __fmul_rn(f.p[4], s.c));
+    acc = __fsub_rn(acc, __fmul_rn(f.p[5], s.d));
+    const float y = __fdiv_rn(acc, f.p[3]);
+    s.b = s.a; s.d = s.c; s.a = x; s.c = y;
+    return y;
+}
 
 __device__ __forceinline__ float fx_compressor(float x, const PostFx &f, FxRegs &s) {
     const float ax = fabsf(x);
@@ -62,6 +77,8 @@ __global__ void __launch_bounds__(32 * kPostWarps) k_postchain(const DevRows g, 
 #pragma unroll
         for (int k = 0; k < kMaxPostFx; ++k) {
             regs[k].a = st[4 * k]; regs[k].b = st[4 * k + 1]; regs[k].pos = __float_as_int(st[4 * k + 2]);
+            regs[k].c = regs[k].d = 0.f;
+            if (k < pc.n && pc.fx[k].kind == kFxBiquad) { regs[k].c = st[4 * k + 2]; regs[k].d = st[4 * k + 3]; regs[k].pos = 0; }
             rings[k] = st + ring_off;
             if (k < pc.n && pc.fx[k].kind == kFxLimiter) ring_off += pc.fx[k].delay;
         }
@@ -89,6 +106,8 @@ __global__ void __launch_bounds__(32 * kPostWarps) k_postchain(const DevRows g, 
                     if (x < -1.f) x = -1.f;
                 } else if (f.kind == kFxCompressor) {
                     x = fx_compressor(x, f, regs[k]);
+                } else if (f.kind == kFxBiquad) {
+                    x = fx_biquad(x, f, regs[k]);
                 } else {
                     x = fx_limiter(x, f, regs[k], rings[k]);
                 }
@@ -105,7 +124,10 @@ __global__ void __launch_bounds__(32 * kPostWarps) k_postchain(const DevRows g, 
     }
     if (have_row) {
 #pragma unroll
-        for (int k = 0; k < kMaxPostFx; ++k) { st[4 * k] = regs[k].a; st[4 * k + 1] = regs[k].b; st[4 * k + 2] = __int_as_float(regs[k].pos); }
+        for (int k = 0; k < kMaxPostFx; ++k) {
+            const bool bq = k < pc.n && pc.fx[k].kind == kFxBiquad;
+            st[4 * k] = regs[k].a; st[4 * k + 1] = regs[k].b; st[4 * k + 2] = bq ? regs[k].c : __int_as_float(regs[k].pos); st[4 * k + 3] = regs[k].d;
+        }
     }
 }
 

@@ -185,8 +185,9 @@ class PhaseVocoderBatch:
     def set_postchain(self, chain):
         """FFT-free effects applied to the float32 output rows, in order (pvgpu_batch_set_postchain): a list of
         ("gain", g), ("compressor", dBThreshold, ratio, dBMakeUpGain, attackMs, releaseMs), ("limiter", dBThreshold, dBMakeUpGain,
-        attackMs, releaseMs) -- the reference objects' constructor arguments.  An empty list clears the chain."""
-        kinds = {"gain": _lib.FX_GAIN, "compressor": _lib.FX_COMPRESSOR, "limiter": _lib.FX_LIMITER}
+        attackMs, releaseMs), ("biquad", type, cutoffFreq, q, dBGain) -- the reference objects' constructor arguments;
+        equalizer_chain() expands the equalizer object into biquad entries.  An empty list clears the chain."""
+        kinds = {"gain": _lib.FX_GAIN, "compressor": _lib.FX_COMPRESSOR, "limiter": _lib.FX_LIMITER, "biquad": _lib.FX_BIQUAD}
         arr = (_lib.Fx * max(len(chain), 1))()
         for i, fx in enumerate(chain):
             arr[i].kind = kinds[fx[0]]
@@ -331,3 +332,21 @@ def run_wav_files(pairs, timeratio=1.0, pitchshift=0.0, mode=NORMAL_SHIFT, corem
     if rc != _lib.OK and all(j["status"] == _lib.OK for j in out):
         check(rc)
     return out
+
+
+def equalizer_chain(paramlist=None):
+    """The reference's equalizer object (eight biquad sections, paramlist = [use, cutoff, Q, gain] x 8, None = its defaults)
+    as a list of ("biquad", type, cutoff, q, gain) entries for PhaseVocoderBatch.set_postchain."""
+    arr = (_lib.Fx * 8)()
+    n = C.c_int()
+    pl = None
+    if paramlist is not None:
+        pl = (C.c_float * 32)(*[float(v) for v in paramlist])
+    check(_lib.lib().pvgpu_equalizer_chain(pl, arr, C.byref(n)))
+    return [("biquad", int(arr[i].p[0]), arr[i].p[1], arr[i].p[2], arr[i].p[3]) for i in range(n.value)]
+
+
+def biquad_design(type, sample_rate, cutoff, q, db_gain):
+    c = (C.c_float * 6)()
+    check(_lib.lib().pvgpu_biquad_design(int(type), int(sample_rate), float(cutoff), float(q), float(db_gain), c))
+    return [c[i] for i in range(6)]

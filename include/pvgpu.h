@@ -123,10 +123,17 @@ int pvgpu_batch_run_host(pvgpu_batch *b, const void *const *in_rows, void *const
  *   PVGPU_FX_GAIN        p = {gain}                                                          src/gain/gain.cc
  *   PVGPU_FX_COMPRESSOR  p = {dBThreshold, ratio, dBMakeUpGain, attackTimeMs, releaseTimeMs}  src/dynamics/compressor.cc
  *   PVGPU_FX_LIMITER     p = {dBThreshold, dBMakeUpGain, attackTimeMs, releaseTimeMs}          src/dynamics/limiter.cc (6 ms look-ahead)
- * n_fx = 0 clears the chain; at most 4 effects.  Takes effect at the next run. */
-enum { PVGPU_FX_GAIN = 1, PVGPU_FX_COMPRESSOR = 2, PVGPU_FX_LIMITER = 3 };
-typedef struct pvgpu_fx { int kind; float p[5]; } pvgpu_fx;
+ *   PVGPU_FX_BIQUAD      p = {type, cutoffFreq, q, dBGain}, type = biquadfilter::Type              src/common/filters/biquadfilter.cc
+ *                        (0 highPass, 1 lowShelf, 2 peaking, 3 notch, 4 highShelf, 5 lowPass, 6 / 7 band-pass, 8 allpass)
+ * n_fx = 0 clears the chain; at most 12 effects.  Takes effect at the next run. */
+enum { PVGPU_FX_GAIN = 1, PVGPU_FX_COMPRESSOR = 2, PVGPU_FX_LIMITER = 3, PVGPU_FX_BIQUAD = 4 };
+typedef struct pvgpu_fx { int kind; float p[6]; } pvgpu_fx;
 int pvgpu_batch_set_postchain(pvgpu_batch *b, const pvgpu_fx *chain, int n_fx);
+/* the equalizer object (src/equalizer/equalizer.cc: eight biquad sections in a fixed order, paramlist = {use, cutoff, Q, gain} x 8,
+ * NULL = its defaults) expanded into PVGPU_FX_BIQUAD entries for pvgpu_batch_set_postchain; chain must hold 8 entries */
+int pvgpu_equalizer_chain(const float *paramlist /*[32] or NULL*/, pvgpu_fx *chain /*[8]*/, int *n_fx);
+/* biquadfilter::computeCoeffs: {b0, b1, b2, a0, a1, a2} of one section (needs no GPU) */
+int pvgpu_biquad_design(int type, int sample_rate, float cutoff, float q, float db_gain, float *coeffs /*[6]*/);
 /* counters of the last run: kernels launched, slices per stream, H2D/D2H bytes */
 int pvgpu_batch_stats(const pvgpu_batch *b, int64_t *kernel_launches, int64_t *slices, int64_t *h2d_bytes, int64_t *d2h_bytes);
 int pvgpu_batch_info(const pvgpu_batch *b, pvgpu_info *info);

@@ -2,7 +2,8 @@
 // (src/gain/gain.cc, src/dynamics/{compressor,limiter}.cc) over a planar float32 file in blocks of 480 samples, in place,
 // the way an SDK user chains them behind the phase vocoder (README.md:78-94).  Checker of the post-chain (pv_post.cu).
 //
-// usage: fxref_drv sr ch in.f32 out.f32 { gain G | compressor THR RATIO MAKEUP ATT REL | limiter THR MAKEUP ATT REL } ...
+// usage: fxref_drv sr ch in.f32 out.f32 { gain G | compressor THR RATIO MAKEUP ATT REL | limiter THR MAKEUP ATT REL |
+//                                          biquad TYPE CUTOFF Q GAIN | equalizer default | equalizer P0 ... P31 } ...
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -29,6 +30,14 @@ int main(int argc, char **argv) {
         if (k == "gain" && i + 1 < argc) { chain.emplace_back(new gain(sr, ch, f(1))); i += 2; }
         else if (k == "compressor" && i + 5 < argc) { chain.emplace_back(new compressor(sr, ch, f(1), f(2), f(3), f(4), f(5))); i += 6; }
         else if (k == "limiter" && i + 4 < argc) { chain.emplace_back(new limiter(sr, ch, f(1), f(2), f(3), f(4))); i += 5; }
+        else if (k == "biquad" && i + 4 < argc) { chain.emplace_back(new biquadfilter(sr, ch, (biquadfilter::Type)atoi(argv[i + 1]), f(2), f(3), f(4))); i += 5; }
+        else if (k == "equalizer" && i + 1 < argc && std::string(argv[i + 1]) == "default") { chain.emplace_back(new equalizer(sr, ch)); i += 2; }
+        else if (k == "equalizer" && i + 32 < argc) {
+            float pl[32];
+            for (int j = 0; j < 32; ++j) pl[j] = f(1 + j);
+            chain.emplace_back(new equalizer(sr, ch, pl));
+            i += 33;
+        }
         else { fprintf(stderr, "bad effect spec at '%s'\n", argv[i]); return 2; }
     }
     const int B = 480;

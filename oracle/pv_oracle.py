@@ -216,13 +216,17 @@ def have_ref_fx() -> bool:
 
 
 def run_ref_fx(x: np.ndarray, sr: int, chain) -> np.ndarray:
-    """chain: list of ("gain", g) / ("compressor", thr, ratio, makeup, att, rel) / ("limiter", thr, makeup, att, rel), applied in
-    order by the unmodified reference's objects (blocks of 480 samples, in place)."""
+    """chain: list of ("gain", g) / ("compressor", thr, ratio, makeup, att, rel) / ("limiter", thr, makeup, att, rel) /
+    ("biquad", type, cutoff, q, gain) / ("equalizer",) (defaults) / ("equalizer", p0 .. p31), applied in order by the unmodified
+    reference's objects (blocks of 480 samples, in place)."""
     x = np.ascontiguousarray(x, dtype=np.float32)
     ch = x.shape[0]
     args = []
     for fx in chain:
-        args += [fx[0]] + [repr(float(v)) for v in fx[1:]]
+        if fx[0] == "equalizer" and len(fx) == 1:
+            args += ["equalizer", "default"]
+        else:
+            args += [fx[0]] + [repr(float(v)) for v in fx[1:]]
     with tempfile.TemporaryDirectory(prefix="fxref_") as d:
         fi, fo = os.path.join(d, "i.f32"), os.path.join(d, "o.f32")
         x.tofile(fi)

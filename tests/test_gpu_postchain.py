@@ -76,3 +76,34 @@ def test_postchain_time_sliced_host_rows_and_clear(A, oracle):
         b.run_host_rows([X[r].astype(np.int16) for r in range(S)], [q[r] for r in range(S)], A.S16)
     assert e.value.code == _lib.EINVAL
     b.close()
+
+
+EQ_PARAMS = [1, 120, 0.7, 1.0,  1, 300, 0.5, -3.0,  1, 900, 1.2, 4.0,  0, 2000, 0.3, 1.5,
+             1, 3100, 2.0, -5.0,  1, 4500, 0.9, 2.5,  1, 7000, 0.6, 3.0,  1, 12000, 0.8, 1.0]
+
+
+@pytest.mark.parametrize("spec", ["default", "all-bands", "sections"])
+def test_equalizer_and_biquads_match_reference_objects(A, oracle, spec):
+    """The 8-band equalizer object (src/equalizer/equalizer.cc) and single biquad sections of every type
+    (src/common/filters/biquadfilter.cc), expanded into the post-chain, against the reference's own objects."""
+    if not (oracle.have_ref() and oracle.have_ref_fx()):
+        pytest.skip("oracle/_ref binaries were not built")
+    sr, ch = 44100, 2
+    if spec == "default":
+        chain, ref_chain = A.equalizer_chain(), [("equalizer",)]
+        assert [c[1] for c in chain] == [0]                       # only the 200 Hz high-pass is on by default
+    elif spec == "all-bands":
+        chain, ref_chain = A.equalizer_chain(EQ_PARAMS), [tuple(["equalizer"] + EQ_PARAMS)]
+        assert [c[1] for c in chain] == [0, 1, 2, 2, 2, 4, 5]
+    else:
+        chain = [("biquad", t, 500.0 + 400.0 * t, 0.8, 3.0) for t in (3, 6, 7, 8)] + [("gain", 0.9)]
+        ref_chain = chain
+    xs = [make_input("x", sr, ch, 0.8 - 0.3 * i, 3100 + i) for i in range(2)]
+    ref = [oracle.run_ref_fx(oracle.run_ref(x, sr, semitones=4.0), sr, ref_chain) for x in xs]
+    b = A.PhaseVocoderBatch(len(xs), xs[0].shape[1], sr, ch, 1.0, 4.0)
+    b.tune(frames_per_chunk=16)
+    b.set_postchain(chain)
+    ys = b.run(xs)
+    b.close()
+    for i, (y, r) in enumerate(zip(ys, ref)):
+        assert_parity(y, r, f"{spec}[{i}]")

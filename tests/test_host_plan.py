@@ -139,3 +139,29 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert "pv_oracle" not in txt and "libpv_oracle" not in txt and "oracle/" not in txt.replace("the CPU oracle", ""), os.path.join(base, f)
+
+
+def test_biquad_design_matches_the_cookbook(pvlib):
+    """pvgpu_biquad_design restates biquadfilter::computeCoeffs (the RBJ audio-EQ-cookbook sections): checked against the
+    closed forms in double precision, and structurally (unity DC gain of a low-pass, unity Nyquist gain of a high-pass)."""
+    import math
+    import audiomod_b200 as A
+    sr = 44100
+    for f0, q, g in ((200.0, 0.3, 1.0), (1000.0, 0.707, -6.0), (8000.0, 2.0, 4.5)):
+        w = 2 * math.pi * f0 / sr
+        al = math.sin(w) / 2 / q
+        a = 10 ** (g / 40)
+        want = {5: [(1 - math.cos(w)) / 2, 1 - math.cos(w), (1 - math.cos(w)) / 2, 1 + al, -2 * math.cos(w), 1 - al],
+                0: [(1 + math.cos(w)) / 2, -(1 + math.cos(w)), (1 + math.cos(w)) / 2, 1 + al, -2 * math.cos(w), 1 - al],
+                2: [1 + al * a, -2 * math.cos(w), 1 - al * a, 1 + al / a, -2 * math.cos(w), 1 - al / a],
+                8: [1 - al, -2 * math.cos(w), 1 + al, 1 + al, -2 * math.cos(w), 1 - al]}
+        for t, c in want.items():
+            got = A.biquad_design(t, sr, f0, q, g)
+            assert np.allclose(got, c, rtol=2e-6, atol=1e-7), (t, got, c)
+        lp, hp = A.biquad_design(5, sr, f0, q, g), A.biquad_design(0, sr, f0, q, g)
+        # float32 coefficients: the sums cancel down to 2(1 - cos w) ~ 8e-4 at 200 Hz, so a few 1e-4 relative is rounding
+        assert abs(sum(lp[:3]) / sum(lp[3:]) - 1) < 1e-3
+        assert abs((hp[0] - hp[1] + hp[2]) / (hp[3] - hp[4] + hp[5]) - 1) < 1e-3
+    with pytest.raises(A.PvgpuError):
+        A.biquad_design(9, sr, 100.0, 1.0, 0.0)
+    assert len(A.equalizer_chain()) == 1 and len(A.equalizer_chain([1, 100, 1, 0] * 8)) == 8
