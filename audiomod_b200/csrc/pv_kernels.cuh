@@ -91,7 +91,7 @@ void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag,
 // interpolation fraction of each entry (interpolated mode) or the table phase as raw bits (direct mode).
 constexpr int kMaxBuckets = 8;      // resampler table phases (oversample <= 8 at quality 4)
 constexpr int kResPerThread = 4;    // outputs a thread of k_ola_resample accumulates at once
-constexpr int kResBlock = 32 * kResPerThread;   // entries of a full warp step; the bank-aware ordering works on two of these at a time
+constexpr int kResBlock = 32 * kResPerThread;   // entries of a full warp step (the bank-aware ordering permutes a whole bucket of a run)
 constexpr int kResPad = 1024;       // bias that keeps the packed tap-0 offset non-negative at the start of a stream
 struct ResampleRun {
     int64_t u_lo;        // first normalised-stream position the run reads (clipped to 0)
@@ -117,6 +117,11 @@ size_t lock_smem_bytes(const DevPlan &p, int channels, int maxpk);
 void launch_ola_resample(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base,
                          long k0, int nframes, int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac,
                          const unsigned *rs_steps, long run_origin, cudaStream_t st);
+// The same stage as a persistent, warp-specialised kernel (pv_ola_ws.cu): producer warps build the normalised stream of the next
+// run while consumer warps filter the current one.  false: no such kernel for this plan (launch k_ola_resample instead).
+bool launch_ola_resample_ws(const DevPlan &p, const DevRows &g, const SliceRec *recs, const float *norm, int64_t norm_base, long recs_base, long k0, int nframes,
+                            int run, int max_consumed, const ResampleRun *runs, const unsigned *rs_ent, const float *rs_frac, const unsigned *rs_steps,
+                            long run_origin, cudaStream_t st, cudaError_t *err);
 // Fused inverse FFT + window + overlap-add + normalisation + resampler (k_synth_ola, pv_fused.cu): one CTA per row runs the
 // frames [k0, k0 + nf) of a chunk in order, `run` frames per round (a multiple of the frames it has in flight).
 struct FusedArgs {

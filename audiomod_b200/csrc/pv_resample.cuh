@@ -4,7 +4,7 @@
 // The host has bucketed the outputs of a run of slices by their table phase (`offset` in resample.c:470), padded every bucket
 // to whole rows of 32 entries and cut it into steps of up to kResPerThread rows (ResampleRun + step list, pv_kernels.cuh).
 // A warp step therefore works on one phase: the sinc "quad" (tab[e-2], tab[e-1], tab[e], tab[e+1]) of every tap is a single
-// broadcast shared-memory access that feeds 4 FMAs per row, and the host orders the entries so that the 32 input windows of a
+// broadcast shared-memory access that feeds 4 FMAs (two packed FFMA2) per row, and the host orders the entries so that the 32 input windows of a
 // row start on different banks.  (Buckets used to be padded to whole 128-entry steps: 13 % dead lanes at 16 slices per run,
 // 50 % at the 8 slices per run the fused kernel prefers; now only the last row of a bucket has dead lanes.)
 #pragma once
@@ -12,6 +12,18 @@
 #include "pv_synth.cuh"
 
 namespace pvgpu {
+
+// Two fp32 FMAs in one instruction (sm_100 FFMA2): acc.{x,y} = x * t.{x,y} + acc.{x,y}, each half rounded exactly like a scalar
+// fma.rn.  ptxas folds the (x, x) pair into the instruction's scalar-broadcast operand form (FFMA2 Rd, Rx.F32, Rt.F32x2, Rd.F32x2),
+// so a tap costs two issue slots per output instead of four.
+__device__ __forceinline__ void ffma2_bcast(float2 &acc, float x, float tx, float ty) {
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(x));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(tx), "f"(ty));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(c));
+}
 
 // One warp step: ROWS rows of 32 outputs of ONE table phase.  The quad of a tap is loaded once (a broadcast) and feeds
 // 4 x ROWS FMAs; two taps per stage, two stages in flight: the loads of the next stage are issued before the FMAs of the
@@ -43,9 +55,9 @@ __device__ __forceinline__ void resample_step(const DevPlan &p, const DevRows &g
     }
     const int qoff = 4 + OV - bucket;
     auto quad_at = [&](int tap) -> float4 { return s_quad[qoff + tap * OV]; };   // warp-uniform: a broadcast load
-    float acc[ROWS][4];
+    float2 acc[ROWS][2];   // (accum[0], accum[1]) and (accum[2], accum[3]) of resample.c:478-489, as FFMA2 register pairs
 #pragma unroll
-    for (int u = 0; u < ROWS; ++u) { acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f; }
+    for (int u = 0; u < ROWS; ++u) { acc[u][0] = make_float2(0.f, 0.f); acc[u][1] = make_float2(0.f, 0.f); }
     float4 tqa[2], tqb[2];
     float xa[2][ROWS], xb[2][ROWS];
     auto load2 = [&](int j, float4 (&tq)[2], float (&x)[2][ROWS]) {
@@ -61,10 +73,8 @@ __device__ __forceinline__ void resample_step(const DevPlan &p, const DevRows &g
         for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
             for (int u = 0; u < ROWS; ++u) {
-                acc[u][0] += x[jj][u] * tq[jj].x;
-                acc[u][1] += x[jj][u] * tq[jj].y;
-                acc[u][2] += x[jj][u] * tq[jj].z;
-                acc[u][3] += x[jj][u] * tq[jj].w;
+                ffma2_bcast(acc[u][0], x[jj][u], tq[jj].x, tq[jj].y);
+                ffma2_bcast(acc[u][1], x[jj][u], tq[jj].z, tq[jj].w);
             }
     };
     load2(0, tqa, xa);
@@ -84,7 +94,7 @@ __device__ __forceinline__ void resample_step(const DevPlan &p, const DevRows &g
         const float i1 = frac + 0.5f * frac * frac - 0.5f * frac * frac * frac;
         const float i3 = -0.33333f * frac + 0.5f * frac * frac - 0.16667f * frac * frac * frac;
         const float i2 = (float)(1. - i0 - i1 - i3);
-        pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), (i0 * acc[u][0]) + (i1 * acc[u][1]) + (i2 * acc[u][2]) + (i3 * acc[u][3]));
+        pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), (i0 * acc[u][0].x) + (i1 * acc[u][0].y) + (i2 * acc[u][1].x) + (i3 * acc[u][1].y));
     }
 }
 
