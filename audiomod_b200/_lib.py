@@ -55,6 +55,8 @@ SYMBOLS = {
     "pvgpu_describe": (C.c_int, [C.POINTER(Config), C.POINTER(Info)]),
     "pvgpu_plan_counts": (C.c_int, [C.POINTER(Config), C.c_int64, C.c_int, _i64p, _i64p, _i64p]),
     "pvgpu_create": (C.c_int, [C.POINTER(Config), _vpp]),
+    "pvgpu_create_multi": (C.c_int, [C.POINTER(Config), C.c_int, _vpp]),
+    "pvgpu_stream_count": (C.c_int, [C.c_void_p]),
     "pvgpu_destroy": (None, [C.c_void_p]),
     "pvgpu_process": (C.c_int, [C.c_void_p, _fpp, C.c_int]),
     "pvgpu_available": (C.c_int, [C.c_void_p]),

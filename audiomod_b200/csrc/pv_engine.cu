@@ -7,16 +7,21 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <exception>
+#include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pvgpu.h"
@@ -1469,67 +1474,245 @@ int pvgpu_test_princarg(int device, int64_t n, const double *a, double *out) {
 // lets the scheduler decide which slices that call runs (exactly the reference's block loop), runs
 // those frames on the device and moves the produced samples into a host FIFO.
 // ------------------------------------------------------------------------------------------------
+// Small persistent pool for the per-row host copies of a live batch (thousands of rows per call: a single thread moves them at
+// ~6 GB/s, which is what bounds the call).  run(n, f) calls f(i) for i in [0, n) on the workers and the caller.
+struct RowPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    std::function<void(size_t)> fn;
+    size_t n = 0, next = 0, chunk = 1, pending = 0;
+    uint64_t gen = 0;
+    bool stop = false;
+    ~RowPool() {
+        { std::lock_guard<std::mutex> l(m); stop = true; }
+        cv_go.notify_all();
+        for (auto &t : workers) t.join();
+    }
+    void start(int nthreads) {
+        for (int i = 0; i < nthreads; ++i)
+            workers.emplace_back([this]() {
+                uint64_t seen = 0;
+                std::unique_lock<std::mutex> l(m);
+                for (;;) {
+                    cv_go.wait(l, [&]() { return stop || gen != seen; });
+                    if (stop) return;
+                    seen = gen;
+                    drain(l);
+                    if (--pending == 0) cv_done.notify_one();
+                }
+            });
+    }
+    void drain(std::unique_lock<std::mutex> &l) {   // called with the lock held
+        while (next < n) {
+            const size_t a = next, b = std::min(n, a + chunk);
+            next = b;
+            l.unlock();
+            for (size_t i = a; i < b; ++i) fn(i);
+            l.lock();
+        }
+    }
+    template <typename F> void run(size_t count, size_t bytes_per_item, F &&f) {
+        if (workers.empty() || count * bytes_per_item < ((size_t)1 << 20)) { for (size_t i = 0; i < count; ++i) f(i); return; }
+        std::unique_lock<std::mutex> l(m);
+        fn = std::forward<F>(f);
+        n = count; next = 0; chunk = std::max<size_t>(1, count / (4 * (workers.size() + 1)));
+        pending = workers.size();
+        ++gen;
+        cv_go.notify_all();
+        drain(l);
+        cv_done.wait(l, [&]() { return pending == 0; });
+    }
+};
+
+// Output FIFO of a streaming instance: every row holds the same number of samples (the rows advance in lock-step), so it is
+// one [rows][cap] block with a common read position -- a ring (cap a power of two), no per-row containers, no compaction.
+// The block is page-locked when it can be: the device-to-host copy of a call's output lands in the ring directly.
+struct RowFifo {
+    float *buf = nullptr;
+    bool pinned = false;
+    size_t rows = 0, cap = 0, rd = 0, count = 0;
+    ~RowFifo() { release(); }
+    void release() { if (buf) { if (pinned) cudaFreeHost(buf); else std::free(buf); } buf = nullptr; cap = 0; }
+    void init(size_t rows_) { release(); rows = rows_; rd = count = 0; }
+    static float *alloc(size_t bytes, bool *pinned) {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) { *pinned = true; return (float *)p; }
+        cudaGetLastError();
+        *pinned = false;
+        return (float *)std::malloc(bytes);
+    }
+    // only between calls (no copy in flight)
+    bool reserve(size_t need) {
+        if (need <= cap) return true;
+        size_t ncap = cap ? cap : 4096;
+        while (ncap < need) ncap *= 2;
+        bool np = false;
+        float *nb = alloc(sizeof(float) * rows * ncap, &np);
+        if (!nb) return false;
+        for (size_t r = 0; r < rows; ++r)
+            for (size_t i = 0; i < count; ++i) nb[r * ncap + i] = buf[r * cap + ((rd + i) & (cap - 1))];
+        release();
+        buf = nb; pinned = np; cap = ncap; rd = 0;
+        return true;
+    }
+    // where the next n samples of every row go: [w, w + first) and, if the ring wraps, [0, n - first); call after reserve
+    void write_span(size_t n, size_t *w, size_t *first) const { *w = (rd + count) & (cap - 1); *first = std::min(n, cap - *w); }
+    void commit(size_t n) { count += n; }
+    // remove the oldest k samples of every row into out[r]
+    void pop(float *const *out, size_t k, RowPool &pool) {
+        if (k == 0) return;
+        const size_t first = std::min(k, cap - rd);
+        pool.run(rows, sizeof(float) * k, [&, first, k](size_t r) {
+            std::memcpy(out[r], &buf[r * cap + rd], sizeof(float) * first);
+            if (first < k) std::memcpy(out[r] + first, &buf[r * cap], sizeof(float) * (k - first));
+        });
+        rd = (rd + k) & (cap - 1);
+        count -= k;
+        if (count == 0) rd = 0;
+    }
+};
+
 struct pvgpu_stream {
     pvgpu_config cfg{};
+    int S = 1;                             // streams advancing in lock-step (pvgpu_create_multi); rows = S * channels, stream-major
+    int R() const { return S * cfg.channels; }
+    std::vector<int64_t> lim;              // per-row limits staged for every call
     Pipeline pl;
     std::unique_ptr<Scheduler> sched;
     std::unique_ptr<Carrier> carrier;
     GlibcRand rng;
     Workspace ws;
-    std::vector<std::vector<float>> tail;  // per channel: input samples from in_base on
+    // input fed by calls that completed no slice (not yet on the device): [rows][pend_cap], pend_len valid per row
+    std::vector<float> pend;
+    size_t pend_cap = 0, pend_len = 0;
+    void pend_append(const float *const *in, size_t n) {
+        const size_t R_ = (size_t)R();
+        if (pend_len + n > pend_cap) {
+            size_t ncap = pend_cap ? pend_cap : 1024;
+            while (ncap < pend_len + n) ncap *= 2;
+            std::vector<float> nb(R_ * ncap);
+            for (size_t r = 0; r < R_; ++r) std::memcpy(&nb[r * ncap], pend.data() + r * pend_cap, sizeof(float) * pend_len);
+            pend.swap(nb);
+            pend_cap = ncap;
+        }
+        for (size_t r = 0; r < R_; ++r) std::memcpy(&pend[r * pend_cap + pend_len], in[r], sizeof(float) * n);
+        pend_len += n;
+    }
+    // The input window [in_base, in_base + dev_len) lives on the device, in one of two buffers of in_cap floats per row: a call
+    // uploads only the samples it was fed and compacts the still-needed part into the other buffer on the device.
+    DevBuf d_inbuf[2];
+    int cur_in = 0;
+    int64_t in_cap = 0, dev_len = 0;
     std::vector<float> car_tail;
     int64_t in_base = 0;
-    std::vector<std::vector<float>> fifo;  // per channel output FIFO (the reference's outbuf ring)
-    size_t fifo_rd = 0;
+    RowFifo fifo;                          // output FIFO of all rows (the reference's outbuf ring)
+    RowPool pool;                          // host copies of a live batch's rows
+    double tr_us[6] = {}, tr_dev[4] = {};  // PVGPU_STREAM_TRACE=1: accumulated microseconds per phase of a call (host) and per device phase
+    cudaEvent_t tr_ev[7] = {};
+    double tr_dev2[2] = {};
+    long tr_calls = 0;
     int num_res = 0;
-    DevBuf d_in, d_out, d_car, d_len;
-    std::vector<float> h_stage, scratch;
+    DevBuf d_out, d_car, d_len, d_stage;
+    std::vector<float> h_stage, h_pack, scratch;
     PinnedArena arena;
     cudaStream_t st = nullptr;
     static constexpr int kF = 64;
-    ~pvgpu_stream() { if (st) cudaStreamDestroy(st); }
+    ~pvgpu_stream() { if (st) cudaStreamDestroy(st); for (auto e : tr_ev) if (e) cudaEventDestroy(e); }
 };
 
 // One pvgpu_process call that completed `added` new slices starting at slice k0.  Steady state: no heap allocation (the
 // vectors keep their capacity), every upload goes through the page-locked arena, one stream synchronisation at the end.
-static int stream_run_new(pvgpu_stream *s, long k0, int added) {
+static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *const *in, int n_new) {
     Pipeline &pl = s->pl;
     Scheduler &sc = *s->sched;
     const DevPlan &p = pl.p;
-    const int C = s->cfg.channels;
+    const int C = s->cfg.channels, R = s->R();
     CU(cudaSetDevice(pl.device));
-    const int64_t len = (int64_t)s->tail[0].size();
-    const int64_t in_stride = std::max<int64_t>((len + 3) & ~(int64_t)3, 4);
+    static const bool trace = []() { const char *v = std::getenv("PVGPU_STREAM_TRACE"); return v && v[0] == '1'; }();
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = trace ? now() : 0.0;
+    double t_mark = t_start;
+    auto mark = [&](int i) { if (trace) { const double t = now(); s->tr_us[i] += t - t_mark; t_mark = t; } };
+    if (trace && !s->tr_ev[0]) for (auto &e : s->tr_ev) cudaEventCreate(&e);
+    if (trace) cudaEventRecord(s->tr_ev[0], s->st);
+    if (trace) cudaEventRecord(s->tr_ev[6], s->st);
+    const int64_t pend = (int64_t)s->pend_len + n_new;   // earlier calls' samples that completed no slice + this call's
+    const int64_t len = s->dev_len + pend;
     const SliceRec &first = sc.recs()[k0 - sc.recs_base()];
     const int64_t out_base = first.out_off;
     const int64_t new_out = sc.total_out() - out_base;
     const int64_t out_stride = std::max<int64_t>((new_out + 3) & ~(int64_t)3, 4);
     {   // room for everything this call stages (nothing is in flight between calls)
         const size_t lists = p.rs_active ? (size_t)(new_out + 8 * 32 * ((added + 3) / 4 + 1) + 64) * 12 + (size_t)added * sizeof(ResampleRun) : 0;
-        const size_t need = sizeof(float) * ((size_t)C * len + s->car_tail.size() + sc.norm().size() + (size_t)C * new_out) + sizeof(SliceRec) * sc.recs().size() +
-                            lists + (pl.d.whisper ? sizeof(float) * (size_t)added * C * p.H : 0) + 64 * 16 + sizeof(int64_t) * (2 * C + 1);
+        const size_t need = sizeof(float) * ((size_t)R * (pend + 16) + s->car_tail.size() + sc.norm().size()) + sizeof(SliceRec) * sc.recs().size() +
+                            lists + (pl.d.whisper ? sizeof(float) * (size_t)added * C * p.H : 0) + 64 * 16 + sizeof(int64_t) * (2 * R + 1);
         s->arena.reserve(need);
         pl.arena = &s->arena;
         pl.staged_all = true;
     }
     int rc;
-    CU(s->d_in.ensure(sizeof(float) * (size_t)C * in_stride));
-    for (int c = 0; c < C; ++c)
-        if ((rc = pl.h2d(s->d_in.as<float>() + c * in_stride, s->tail[c].data(), sizeof(float) * len, s->st))) return rc;
-    // per-row limits: [0..C) valid input end, [C..2C) output limit, [2C] carrier length
-    int64_t lim[2 * 16 + 1];
-    for (int c = 0; c < C; ++c) { lim[c] = s->in_base + len; lim[C + c] = INT64_MAX; }
-    lim[2 * C] = s->in_base + (int64_t)s->car_tail.size();
-    CU(s->d_len.ensure(sizeof(int64_t) * (2 * 16 + 1)));
-    if ((rc = pl.h2d(s->d_len.p, lim, sizeof(int64_t) * (2 * C + 1), s->st))) return rc;
+    if (len > s->in_cap) {   // grow both window buffers (rare: the window is bounded by the FFT size plus one call's input)
+        const int64_t cap = (std::max<int64_t>(2 * s->in_cap, len + 4096) + 3) & ~(int64_t)3;
+        DevBuf grown;
+        CU(grown.ensure(sizeof(float) * (size_t)R * cap));
+        if (s->dev_len > 0)
+            CU(cudaMemcpy2DAsync(grown.p, sizeof(float) * cap, s->d_inbuf[s->cur_in].p, sizeof(float) * s->in_cap, sizeof(float) * s->dev_len, R, cudaMemcpyDeviceToDevice, s->st));
+        CU(cudaStreamSynchronize(s->st));
+        std::swap(s->d_inbuf[s->cur_in].p, grown.p);
+        std::swap(s->d_inbuf[s->cur_in].bytes, grown.bytes);
+        s->d_inbuf[s->cur_in ^ 1].release();
+        CU(s->d_inbuf[s->cur_in ^ 1].ensure(sizeof(float) * (size_t)R * cap));
+        s->in_cap = cap;
+    }
+    const int64_t in_stride = s->in_cap;
+    float *d_in = s->d_inbuf[s->cur_in].as<float>();
+    if (pend > 0) {
+        // all rows' new samples straight from the caller's rows into one page-locked block, one copy (a live batch of thousands
+        // of rows must not issue a copy per row); without page-locked memory the same block is pageable and the copy synchronous
+        const int64_t pp = (pend + 15) & ~(int64_t)15;   // packed row pitch: rows start on 64-byte lines
+        float *pin = (float *)s->arena.take(sizeof(float) * (size_t)R * pp);
+        const bool locked = pin != nullptr;
+        if (!pin) { s->h_pack.resize((size_t)R * pp); pin = s->h_pack.data(); }
+        const size_t pl_ = s->pend_len;
+        // non-temporal stores: the copy engine reads this block next, and lines left dirty in several cores' caches slow it 4-7x
+        s->pool.run((size_t)R, sizeof(float) * (size_t)pend, [&, pl_, pin, pp, locked](size_t r) {
+            if (locked) {
+                if (pl_) copy_nt(pin + r * pp, s->pend.data() + r * s->pend_cap, pl_);
+                if (n_new) copy_nt(pin + r * pp + pl_, in[r], (size_t)n_new);
+                copy_nt_fence();
+            } else {
+                if (pl_) std::memcpy(pin + r * pp, s->pend.data() + r * s->pend_cap, sizeof(float) * pl_);
+                if (n_new) std::memcpy(pin + r * pp + pl_, in[r], sizeof(float) * (size_t)n_new);
+            }
+        });
+        mark(0);   // pack
+        if (trace) cudaEventRecord(s->tr_ev[5], s->st);
+        if (R >= 64) {
+            // many short rows: one contiguous copy over PCIe, then the pitched placement on the device (a host-to-device 2-D copy
+            // of 4096 rows of 1.9 KB to 4-byte-aligned destinations ran at 7 GB/s, and so did the device-to-device one)
+            CU(s->d_stage.ensure(sizeof(float) * (size_t)R * pp));
+            CU(cudaMemcpyAsync(s->d_stage.p, pin, sizeof(float) * (size_t)R * pp, cudaMemcpyHostToDevice, s->st));
+            launch_place_rows(d_in + s->dev_len, in_stride, s->d_stage.as<float>(), pp, (int)pend, R, s->st);
+        } else {
+            CU(cudaMemcpy2DAsync(d_in + s->dev_len, sizeof(float) * in_stride, pin, sizeof(float) * pp, sizeof(float) * pend, R, cudaMemcpyHostToDevice, s->st));
+        }
+        if (trace) cudaEventRecord(s->tr_ev[6], s->st);   // input placed
+    }
+    // per-row limits: [0..R) valid input end, [R..2R) output limit, [2R] carrier length
+    s->lim.resize(2 * (size_t)R + 1);
+    for (int r = 0; r < R; ++r) { s->lim[r] = s->in_base + len; s->lim[R + r] = INT64_MAX; }
+    s->lim[2 * R] = s->in_base + (int64_t)s->car_tail.size();
+    CU(s->d_len.ensure(sizeof(int64_t) * (2 * (size_t)R + 1)));
+    if ((rc = pl.h2d(s->d_len.p, s->lim.data(), sizeof(int64_t) * (2 * (size_t)R + 1), s->st))) return rc;
     if ((rc = pl.upload_schedule(sc, s->st))) return rc;
     if ((rc = pl.build_resample_runs(k0, k0 + added, pl.fused ? pl.fa.run : ola_run_limit(p, 8, pl.max_consumed, pl.max_out), s->st))) return rc;
-    CU(s->d_out.ensure(sizeof(float) * (size_t)C * out_stride));
+    CU(s->d_out.ensure(sizeof(float) * (size_t)R * out_stride));
     if (!pl.fused && halo_of(sc.recs(), sc.recs_base(), p.rs_active ? (int)p.rs_filt_len : 1) > s->ws.Fr - s->ws.F) return fail(PVGPU_ESTATE, "too many overlapping (dropped) slices; retrieve output more often");
     DevRows g{};
-    g.rows = C; g.channels = C;
-    g.in = s->d_in.as<float>(); g.in_stride = in_stride; g.in_base = s->in_base;
-    g.n_in = s->d_len.as<int64_t>(); g.n_out = s->d_len.as<int64_t>() + C;
+    g.rows = R; g.channels = C;
+    g.in = d_in; g.in_stride = in_stride; g.in_base = s->in_base;
+    g.n_in = s->d_len.as<int64_t>(); g.n_out = s->d_len.as<int64_t>() + R;
     g.out = s->d_out.as<float>(); g.out_stride = out_stride; g.out_base = out_base;
     s->ws.bind(pl, g);
     g.aux_base = k0;
@@ -1550,28 +1733,45 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
         CU(pl.b_carph.ensure(sizeof(float) * (size_t)added * p.Hp));
         DevRows gc{};
         gc.rows = 1; gc.channels = 1;
-        gc.in = s->d_car.as<float>(); gc.in_stride = 0; gc.in_base = s->in_base; gc.n_in = s->d_len.as<int64_t>() + 2 * C;
+        gc.in = s->d_car.as<float>(); gc.in_stride = 0; gc.in_base = s->in_base; gc.n_in = s->d_len.as<int64_t>() + 2 * R;
         gc.mag = pl.b_carmag.as<float>(); gc.phase = pl.b_carph.as<float>(); gc.F = added;
         launch_analyse(p, gc, k0, added, s->st);
     }
+    if (trace) cudaEventRecord(s->tr_ev[1], s->st);   // uploads done
     for (long k = k0; k < k0 + added; k += s->ws.F)
         if ((rc = pl.run_frames(g, k, (int)std::min<long>(s->ws.F, k0 + added - k), s->st))) return rc;
     CU(cudaGetLastError());
-    const float *h_out = nullptr;
-    if (new_out > 0) {
-        float *pin = (float *)s->arena.take(sizeof(float) * (size_t)C * new_out);
-        if (!pin) { s->h_stage.resize((size_t)C * new_out); pin = s->h_stage.data(); }
-        CU(cudaMemcpy2DAsync(pin, sizeof(float) * new_out, s->d_out.p, sizeof(float) * out_stride, sizeof(float) * new_out, C, cudaMemcpyDeviceToHost, s->st));
-        h_out = pin;
+    if (trace) cudaEventRecord(s->tr_ev[2], s->st);   // kernels done
+    if (new_out > 0) {   // the output goes straight into the (page-locked) FIFO ring
+        if (!s->fifo.reserve(s->fifo.count + (size_t)new_out)) return fail(PVGPU_ENOMEM, "out of host memory");
+        size_t w, first;
+        s->fifo.write_span((size_t)new_out, &w, &first);
+        CU(cudaMemcpy2DAsync(s->fifo.buf + w, sizeof(float) * s->fifo.cap, s->d_out.p, sizeof(float) * out_stride, sizeof(float) * first, R, cudaMemcpyDeviceToHost, s->st));
+        if (first < (size_t)new_out)
+            CU(cudaMemcpy2DAsync(s->fifo.buf, sizeof(float) * s->fifo.cap, s->d_out.as<float>() + first, sizeof(float) * out_stride, sizeof(float) * ((size_t)new_out - first), R,
+                                 cudaMemcpyDeviceToHost, s->st));
     }
-    CU(cudaStreamSynchronize(s->st));   // the call's only synchronisation
-    pl.staged_all = true;
-    for (int c = 0; c < C && new_out > 0; ++c) s->fifo[c].insert(s->fifo[c].end(), h_out + (size_t)c * new_out, h_out + (size_t)(c + 1) * new_out);
-    // forget what no later slice can need
+    if (trace) cudaEventRecord(s->tr_ev[3], s->st);   // output copy done
+    // forget the input no later slice can need: the rest of the window moves to the front of the other buffer, on the device
     const long k_next = k0 + added;
     const int64_t new_base = (int64_t)k_next * p.hop;
     const int64_t dropn = std::min<int64_t>(new_base - s->in_base, len);
-    for (int c = 0; c < C; ++c) s->tail[c].erase(s->tail[c].begin(), s->tail[c].begin() + dropn);
+    const int64_t keep = len - dropn;
+    if (dropn > 0) {
+        if (keep > 0)
+            CU(cudaMemcpy2DAsync(s->d_inbuf[s->cur_in ^ 1].p, sizeof(float) * in_stride, d_in + dropn, sizeof(float) * in_stride, sizeof(float) * keep, R, cudaMemcpyDeviceToDevice, s->st));
+        s->cur_in ^= 1;
+    }
+    if (trace) cudaEventRecord(s->tr_ev[4], s->st);   // window compaction done
+    mark(1);   // enqueue: schedule upload, work lists, launches, copies
+    CU(cudaStreamSynchronize(s->st));   // the call's only synchronisation
+    mark(2);   // device
+    if (trace) for (int i = 0; i < 4; ++i) { float ms = 0; cudaEventElapsedTime(&ms, s->tr_ev[i], s->tr_ev[i + 1]); s->tr_dev[i] += 1e3 * ms; }
+    if (trace && pend > 0) { float ms = 0; cudaEventElapsedTime(&ms, s->tr_ev[0], s->tr_ev[5]); s->tr_dev2[0] += 1e3 * ms; cudaEventElapsedTime(&ms, s->tr_ev[5], s->tr_ev[6]); s->tr_dev2[1] += 1e3 * ms; }
+    pl.staged_all = true;
+    if (new_out > 0) s->fifo.commit((size_t)new_out);
+    s->pend_len = 0;
+    s->dev_len = keep;
     if (pl.d.vocoder) s->car_tail.erase(s->car_tail.begin(), s->car_tail.begin() + std::min<int64_t>(dropn, (int64_t)s->car_tail.size()));
     s->in_base += dropn;
     if (pl.fused) {
@@ -1587,27 +1787,42 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added) {
         while (kh > 0 && recs[kh].res_off > sc.res_total() - L) --kh;
         sc.trim(recs[kh].jlo, recs[kh].ola_off);
     }
+    mark(3);   // trim
+    if (trace && ++s->tr_calls % 50 == 0) {
+        std::fprintf(stderr, "[pvgpu stream trace] rows %d: pack %.1f us, enqueue %.1f, device wait %.1f, trim %.1f | device: uploads %.1f, kernels %.1f, output copy %.1f, window compaction %.1f per call (last 50)\n",
+                     R, s->tr_us[0] / 50, s->tr_us[1] / 50, s->tr_us[2] / 50, s->tr_us[3] / 50, s->tr_dev[0] / 50, s->tr_dev[1] / 50, s->tr_dev[2] / 50, s->tr_dev[3] / 50);
+        for (double &v : s->tr_us) v = 0;
+        std::fprintf(stderr, "[pvgpu stream trace]   of the uploads: until the packed block is ready %.1f us, input copy + placement %.1f\n", s->tr_dev2[0] / 50, s->tr_dev2[1] / 50);
+        s->tr_dev2[0] = s->tr_dev2[1] = 0;
+        for (double &v : s->tr_dev) v = 0;
+    }
     return PVGPU_OK;
 }
 
 extern "C" {
 
-static int pvgpu_create_body(const pvgpu_config *cfg, pvgpu_stream **out);
+static int pvgpu_create_body(const pvgpu_config *cfg, int n_streams, pvgpu_stream **out);
 int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out) {
-    return guarded([&]() -> int { return pvgpu_create_body(cfg, out); });
+    return guarded([&]() -> int { return pvgpu_create_body(cfg, 1, out); });
 }
-static int pvgpu_create_body(const pvgpu_config *cfg, pvgpu_stream **out) {
+int pvgpu_create_multi(const pvgpu_config *cfg, int n_streams, pvgpu_stream **out) {
+    return guarded([&]() -> int { return pvgpu_create_body(cfg, n_streams, out); });
+}
+int pvgpu_stream_count(const pvgpu_stream *s) { return s ? s->S : 0; }
+static int pvgpu_create_body(const pvgpu_config *cfg, int n_streams, pvgpu_stream **out) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!out) return fail(PVGPU_EINVAL, "null out pointer");
+    if (n_streams < 1 || (long)n_streams * cfg->channels > 65535) return fail(PVGPU_EINVAL, "n_streams * channels must be 1..65535");
     std::unique_ptr<pvgpu_stream> s(new (std::nothrow) pvgpu_stream);
     if (!s) return fail(PVGPU_ENOMEM, "out of host memory");
     s->cfg = *cfg;
+    s->S = n_streams;
     if ((rc = s->pl.init(*cfg))) return rc;
     s->sched.reset(new Scheduler(s->pl.d, true));
     if (s->pl.d.vocoder) s->carrier.reset(new Carrier(cfg->sample_rate, cfg->mode == PVGPU_VOCODER_CHORD));
-    s->tail.resize(cfg->channels);
-    s->fifo.resize(cfg->channels);
+    s->fifo.init((size_t)s->R());
+    if (s->R() >= 256) s->pool.start((int)std::min(7u, std::max(1u, std::thread::hardware_concurrency() / 2)));   // live batch: parallel row copies
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     const int halo = 80;
     s->pl.ola_run = 8;
@@ -1624,7 +1839,7 @@ static int pvgpu_create_body(const pvgpu_config *cfg, pvgpu_stream **out) {
         const int overlap = (d.N + min_shift - 1) / min_shift + (s->pl.p.rs_active ? ((int)d.rs.filt_len + min_shift - 1) / min_shift : 0) + 2;
         s->pl.plan_fused(pvgpu_stream::kF, std::max(nominal, 1), out_bound, overlap + 8 <= halo && overlap + 8 <= ola_max_table_slices() - 1);
     }
-    if ((rc = s->ws.ensure(s->pl, cfg->channels, pvgpu_stream::kF, halo))) return rc;
+    if ((rc = s->ws.ensure(s->pl, s->R(), pvgpu_stream::kF, halo))) return rc;
     if ((rc = s->ws.reset_state(s->pl, s->st))) return rc;
     *out = s.release();
     return PVGPU_OK;
@@ -1649,18 +1864,18 @@ int pvgpu_process(pvgpu_stream *s, const float *const *in, int n) {
 static int pvgpu_process_body(pvgpu_stream *s, const float *const *in, int n) {
     if (!s || n < 0 || (n > 0 && !in)) return fail(PVGPU_EINVAL, "bad argument");
     if (!s->pl.d.valid_mode) { s->num_res = 0; return PVGPU_OK; }  // phasevocoder.cc:104-106: unknown mode does nothing
-    const int C = s->cfg.channels;
-    for (int c = 0; c < C; ++c) s->tail[c].insert(s->tail[c].end(), in[c], in[c] + n);
     if (s->carrier) {
         const size_t at = s->car_tail.size();
         s->car_tail.resize(at + n);
         s->carrier->generate(s->car_tail.data() + at, (size_t)n);
     }
     const long k0 = s->sched->recs_base() + s->sched->slices();
-    const int added = s->sched->feed(n);
+    const int added = s->sched->feed(n);   // the schedule does not depend on the data
     if (added > 0) {
-        int rc = stream_run_new(s, k0, added);
+        int rc = stream_run_new(s, k0, added, in, n);
         if (rc) return rc;
+    } else if (n > 0) {
+        s->pend_append(in, (size_t)n);
     }
     s->num_res = (int)s->sched->available();
     return PVGPU_OK;
@@ -1672,13 +1887,9 @@ int pvgpu_retrieve(pvgpu_stream *s, float *const *out, int n) {
     if (!s || n < 0 || (n > 0 && !out)) return -fail(PVGPU_EINVAL, "bad argument");
     long k = std::min<long>(n, s->num_res);  // phasevocoder.cc:111-113
     k = std::min<long>(k, s->sched->available());
-    for (int c = 0; c < s->cfg.channels; ++c) std::memcpy(out[c], s->fifo[c].data() + s->fifo_rd, sizeof(float) * (size_t)k);
-    s->fifo_rd += (size_t)k;
+    k = std::min<long>(k, (long)s->fifo.count);
+    s->fifo.pop(out, (size_t)k, s->pool);
     s->sched->drain(k);
-    if (s->fifo_rd > (1u << 20)) {
-        for (auto &f : s->fifo) f.erase(f.begin(), f.begin() + (long)s->fifo_rd);
-        s->fifo_rd = 0;
-    }
     return (int)k;
 }
 

@@ -154,6 +154,9 @@ int postchain_state_stride(const PostChain &pc);
 void launch_postchain_reset(const PostChain &pc, float *state, int rows, cudaStream_t st);
 void launch_postchain(const DevRows &g, const PostChain &pc, float *state, int64_t col0, int64_t col1, cudaStream_t st);
 
+// row-wise copy with independent pitches and any 4-byte alignment (live batch input placement)
+void launch_place_rows(float *dst, int64_t dst_pitch, const float *src, int64_t src_pitch, int width, int rows, cudaStream_t st);
+
 void launch_test_atan2f(int64_t n, const float *y, const float *x, float *out, cudaStream_t st);
 void launch_test_princarg(int64_t n, const double *a, double *out, cudaStream_t st);
 

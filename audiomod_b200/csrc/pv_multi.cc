@@ -30,6 +30,10 @@
 #include "pv_internal.h"
 #include "pv_plan.h"
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 namespace pvgpu {
 
 // ---- NUMA placement without libnuma -------------------------------------------------------------------------------
@@ -321,3 +325,21 @@ int pvgpu_bind_thread_to_device(int device) {
 }
 
 }  // extern "C"
+
+namespace pvgpu {
+void copy_nt(float *dst, const float *src, size_t n) {
+#if defined(__x86_64__)
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 15)) { _mm_stream_si32((int *)(dst + i), *(const int *)(src + i)); ++i; }
+    for (; i + 4 <= n; i += 4) _mm_stream_ps(dst + i, _mm_loadu_ps(src + i));
+    for (; i < n; ++i) _mm_stream_si32((int *)(dst + i), *(const int *)(src + i));
+#else
+    std::memcpy(dst, src, sizeof(float) * n);
+#endif
+}
+void copy_nt_fence() {
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
+}
+}  // namespace pvgpu

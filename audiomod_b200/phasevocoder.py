@@ -53,22 +53,29 @@ def plan_counts(n_in, sampleRate, numChannels, timeratio, pitchshift, mode=NORMA
 
 
 def _chan_ptrs(a: np.ndarray):
-    arr = (_fp * a.shape[0])()
-    for c in range(a.shape[0]):
-        arr[c] = a[c].ctypes.data_as(_fp)
-    return arr
+    """float** for the rows of a 2-D float32 array (vectorised: a live batch has thousands of rows per call)."""
+    ptrs = (np.uintp(a.ctypes.data) + np.arange(a.shape[0], dtype=np.uintp) * np.uintp(a.strides[0])).astype(np.uintp)
+    return ptrs.ctypes.data_as(C.POINTER(_fp))   # keeps a reference to `ptrs`
 
 
 class phasevocoder:
-    """One stream.  Buffers are planar float32 arrays of shape [numChannels, n]."""
+    """One stream.  Buffers are planar float32 arrays of shape [numChannels, n].
+
+    streams > 1 makes it a live batch (pvgpu_create_multi): `streams` objects of one configuration advancing in lock-step,
+    buffers [streams * numChannels, n] with row = stream * numChannels + channel; every call serves all of them with one set
+    of kernel launches, and every stream gets the samples its own object would."""
 
     def __init__(self, sampleRate, numChannels, timeratio, pitchshift, mode=NORMAL_SHIFT, coremode=PHASE_LOCKED,
-                 fftsize=2048, hopsize=0, device=0):
+                 fftsize=2048, hopsize=0, device=0, streams=1):
         self._h = C.c_void_p()
-        self.num_channels_ = int(numChannels)
+        self.streams_ = int(streams)
+        self.num_channels_ = int(numChannels) * self.streams_    # rows of every buffer
         self._ready = False
-        check(_lib.lib().pvgpu_create(C.byref(_cfg(sampleRate, numChannels, timeratio, pitchshift, mode, coremode, fftsize,
-                                                    hopsize, device)), C.byref(self._h)))
+        cfg = _cfg(sampleRate, numChannels, timeratio, pitchshift, mode, coremode, fftsize, hopsize, device)
+        if self.streams_ == 1:
+            check(_lib.lib().pvgpu_create(C.byref(cfg), C.byref(self._h)))
+        else:
+            check(_lib.lib().pvgpu_create_multi(C.byref(cfg), self.streams_, C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None):

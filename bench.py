@@ -315,6 +315,25 @@ def stream_latency():
         out[name] = {"p50": float(np.percentile(t, 50)), "p99": float(np.percentile(t, 99)), "max": float(t.max()), "calls": int(t.size)}
     out["block_samples"] = 480
     out["block_ms_of_audio"] = 1e3 * 480 / 44100
+    # live batch (pvgpu_create_multi): S cfg4 streams in lock-step through one instance, the same 480-sample blocks; a call serves
+    # all of them.  real_time_streams = how many such streams one GPU keeps up with at this block size (S x block duration / p99).
+    live = {}
+    for S in (64, 1024, 4096):
+        x = np.ascontiguousarray(np.tile(synth(2, 44100, 1.5, 1), (S, 1)))
+        x *= (1.0 + 0.001 * np.arange(S, dtype=np.float32))[:, None]          # distinct rows
+        pv = A.phasevocoder(44100, 1, 1.0, 7.0, 0, 1, 2048, streams=S)
+        times = []
+        for i in range(0, x.shape[1] - B, B):
+            blk = np.ascontiguousarray(x[:, i:i + B])
+            t0 = time.perf_counter()
+            pv.processBlock(blk)
+            times.append(time.perf_counter() - t0)
+        pv.close()
+        t = np.array(times[20:]) * 1e3
+        p50, p99 = float(np.percentile(t, 50)), float(np.percentile(t, 99))
+        live[str(S)] = {"p50": p50, "p99": p99, "max": float(t.max()), "calls": int(t.size), "real_time_streams": int(S * out["block_ms_of_audio"] / p99),
+                        "audio_s_per_s": S * out["block_ms_of_audio"] / p50}
+    out["live_batch_cfg4"] = live
     return out
 
 

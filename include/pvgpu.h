@@ -79,6 +79,14 @@ typedef struct pvgpu_stream pvgpu_stream;
 
 /* phasevocoder::phasevocoder + init (phasevocoder.cc:24-85) */
 int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out);
+/* Live batch: n_streams phasevocoder objects of one configuration advancing in lock-step -- every pvgpu_process /
+ * pvgpu_retrieve / pvgpu_process_block call passes n_streams * channels row pointers (stream-major: row = stream * channels
+ * + channel) and the same n for all of them.  One set of kernel launches and one copy each way per call serve all streams
+ * (the schedule does not depend on the data), so the per-call cost of a real-time block is paid once, not per stream.  Every
+ * stream produces exactly the samples its own pvgpu_create instance would (tests/test_gpu_live_batch.py).
+ * n_streams * channels <= 65535.  pvgpu_stream_count returns n_streams (1 for pvgpu_create). */
+int pvgpu_create_multi(const pvgpu_config *cfg, int n_streams, pvgpu_stream **out);
+int pvgpu_stream_count(const pvgpu_stream *s);
 /* phasevocoder::~phasevocoder (phasevocoder.cc:62-67) */
 void pvgpu_destroy(pvgpu_stream *s);
 /* modbase_offline::processInData (modbase.h:89, phasevocoder.cc:87-108): consume n samples per channel */

@@ -1,0 +1,100 @@
+"""Live batch (pvgpu_create_multi): S phasevocoder objects of one configuration advancing in lock-step through one instance.
+
+Every stream of the live batch must produce, call by call, exactly the samples (and counts) its own single-stream instance
+produces for the same sequence of calls -- and those single-stream instances are the ones the golden / oracle tests pin to
+the reference (tests/test_gpu_parity.py::test_streaming_*).  Checked bit for bit: the live batch runs the same kernels on
+rows = S x channels with the same data-independent schedule."""
+import numpy as np
+import pytest
+
+from cases import CASES, ctor_args, make_input
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def A(pvlib):
+    import audiomod_b200
+    if pvlib.pvgpu_device_count() < 1:
+        pytest.fail("no CUDA device: GPU tests must run on the B200 box")
+    return audiomod_b200
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+LIVE = ["cfg4_shift_p7_mono", "cfg1_shift_p4_stereo", "cfg3_formant_p4", "cfg5_robotic_512", "cfg5_whisper_1024", "cfg5_chord_4096",
+        "cfg2_stretch_1p5_4096", "core0_shift_p3_stereo"]
+
+
+@pytest.mark.parametrize("name", LIVE)
+def test_live_batch_equals_single_instances_call_by_call(A, name):
+    kw, sr, ch, secs, seed = next((c[1], c[2], c[3], c[4], c[5]) for c in CASES if c[0] == name)
+    tr, st, mode, core, fft = ctor_args(kw)
+    S = 5
+    n = int(sr * min(secs, 0.5))
+    xs = [make_input(name, sr, ch, n / sr, seed + 11 * i)[:, :n] for i in range(S)]
+    X = np.ascontiguousarray(np.concatenate(xs, axis=0))           # [S * ch, n], row = stream * ch + channel
+    live = A.phasevocoder(sr, ch, tr, st, mode, core, fft, streams=S)
+    singles = [A.phasevocoder(sr, ch, tr, st, mode, core, fft) for _ in range(S)]
+    sizes = [480, 480, 1, 0, 2048, 311, 4099, 480]
+    pos, k, total = 0, 0, 0
+    while pos < n:
+        m = min(sizes[k % len(sizes)], n - pos)
+        k += 1
+        live.processInData(np.ascontiguousarray(X[:, pos:pos + m]))
+        avail = live.getOutSamples()
+        take = avail if k % 3 else avail // 2                       # sometimes leave samples in the ring
+        Y = live.getOutData(take)
+        assert Y.shape[0] == S * ch
+        for i, pv in enumerate(singles):
+            pv.processInData(np.ascontiguousarray(xs[i][:, pos:pos + m]))
+            assert pv.getOutSamples() == avail, f"{name}: call {k}, stream {i}"
+            y = pv.getOutData(take)
+            assert np.array_equal(_bits(Y[i * ch:(i + 1) * ch]), _bits(y)), f"{name}: call {k}, stream {i} differs from its own instance"
+        total += Y.shape[1]
+        pos += m
+    assert total > 0
+    live.close()
+    for pv in singles:
+        pv.close()
+
+
+def test_live_batch_process_block_protocol(A):
+    """The in-place real-time protocol (processBlock / outputReady, phasevocoder.cc:133-183) on 64 streams at once."""
+    sr, ch, S, B = 44100, 1, 64, 480
+    n = B * 60
+    xs = [make_input("x", sr, ch, n / sr, 7000 + i)[:, :n] for i in range(S)]
+    X = np.ascontiguousarray(np.concatenate(xs, axis=0))
+    live = A.phasevocoder(sr, ch, 1.0, 7.0, streams=S)
+    ref = [A.phasevocoder(sr, ch, 1.0, 7.0) for _ in (0, S // 2, S - 1)]
+    ready_blocks = 0
+    for pos in range(0, n, B):
+        blk = np.ascontiguousarray(X[:, pos:pos + B])
+        before = blk.copy()
+        live.processBlock(blk)
+        for j, i in enumerate((0, S // 2, S - 1)):
+            b1 = np.ascontiguousarray(xs[i][:, pos:pos + B])
+            ref[j].processBlock(b1)
+            assert ref[j].outputReady() == live.outputReady()
+            assert np.array_equal(_bits(blk[i:i + 1]), _bits(b1)), f"block at {pos}, stream {i}"
+        if live.outputReady():
+            ready_blocks += 1
+        else:
+            assert np.array_equal(blk, before), "buffers must be untouched while output is not ready"
+    assert ready_blocks > 40
+    live.close()
+    for pv in ref:
+        pv.close()
+
+
+def test_live_batch_limits(A, pvlib):
+    import ctypes as C
+    from audiomod_b200 import _lib
+    with pytest.raises(A.PvgpuError) as e:
+        A.phasevocoder(44100, 2, 1.0, 4.0, streams=40000)
+    assert e.value.code == _lib.EINVAL
+    pv = A.phasevocoder(44100, 2, 1.0, 4.0, streams=3)
+    assert pvlib.pvgpu_stream_count(pv._h) == 3
+    pv.close()
