@@ -331,7 +331,7 @@ struct Pipeline {
     struct RunScratch {
         std::vector<ResampleRun> runs;
         std::vector<unsigned> ent, steps, run_steps, be[kMaxBuckets], e2;
-        std::vector<float> frac, bf[kMaxBuckets], f2;
+        std::vector<float> frac, coef, bf[kMaxBuckets], f2;
     } rsx;
 
     static int upload(DevBuf &b, const void *src, size_t bytes) {
@@ -487,6 +487,20 @@ struct Pipeline {
         }
         CU(b_runs.ensure(sizeof(ResampleRun) * std::max<size_t>(runs.size(), 1)));
         CU(b_rsent.ensure(sizeof(unsigned) * std::max<size_t>(ent.size(), 1)));
+        if (!p.rs_direct) {   // interpolated table: the four cubic coefficients of every entry (cubic_coef, resample.c:339-351)
+            std::vector<float> &coef = rsx.coef;
+            coef.resize(4 * frac.size());
+            for (size_t i = 0; i < frac.size(); ++i) {
+                const float fr = frac[i];
+                float ip[4];
+                ip[0] = -0.16667f * fr + 0.16667f * fr * fr * fr;
+                ip[1] = fr + 0.5f * fr * fr - 0.5f * fr * fr * fr;
+                ip[3] = -0.33333f * fr + 0.5f * fr * fr - 0.16667f * fr * fr * fr;
+                ip[2] = (float)(1. - ip[0] - ip[1] - ip[3]);
+                std::memcpy(&coef[4 * i], ip, sizeof ip);
+            }
+            frac.swap(coef);   // uploaded below in place of the fractions (the next call clears both)
+        }
         CU(b_rsfrac.ensure(sizeof(float) * std::max<size_t>(frac.size(), 1)));
         CU(b_rssteps.ensure(sizeof(unsigned) * std::max<size_t>(steps.size(), 1)));
         int rc;
@@ -1644,7 +1658,7 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *cons
     const int64_t new_out = sc.total_out() - out_base;
     const int64_t out_stride = std::max<int64_t>((new_out + 3) & ~(int64_t)3, 4);
     {   // room for everything this call stages (nothing is in flight between calls)
-        const size_t lists = p.rs_active ? (size_t)(new_out + 8 * 32 * ((added + 3) / 4 + 1) + 64) * 12 + (size_t)added * sizeof(ResampleRun) : 0;
+        const size_t lists = p.rs_active ? (size_t)(new_out + 8 * 32 * ((added + 3) / 4 + 1) + 64) * 24 + (size_t)added * sizeof(ResampleRun) : 0;
         const size_t need = sizeof(float) * ((size_t)R * (pend + 16) + s->car_tail.size() + sc.norm().size()) + sizeof(SliceRec) * sc.recs().size() +
                             lists + (pl.d.whisper ? sizeof(float) * (size_t)added * C * p.H : 0) + 64 * 16 + sizeof(int64_t) * (2 * R + 1);
         s->arena.reserve(need);

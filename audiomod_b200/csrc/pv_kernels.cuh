@@ -87,8 +87,8 @@ void launch_synthesise(const DevPlan &p, const DevRows &g, const float *car_mag,
                        long k0, int nframes, cudaStream_t st);
 // Host-built work list of the resampler for one run of slices (see k_ola_resample): the run's outputs bucketed by
 // sinc-table phase, output order inside a bucket, buckets padded to multiples of kResBlock.  Entry = (tap-0 position relative to
-// u_lo + kResPad) << 16 | (output position relative to out_first); 0xffffffff = padding.  rs_frac holds the cubic
-// interpolation fraction of each entry (interpolated mode) or the table phase as raw bits (direct mode).
+// u_lo + kResPad) << 16 | (output position relative to out_first); 0xffffffff = padding.  rs_frac holds the four cubic
+// interpolation coefficients of each entry (interpolated mode, 16 bytes) or the table phase as raw bits (direct mode, 4 bytes).
 constexpr int kMaxBuckets = 8;      // resampler table phases (oversample <= 8 at quality 4)
 constexpr int kResPerThread = 4;    // outputs a thread of k_ola_resample accumulates at once
 constexpr int kResBlock = 32 * kResPerThread;   // entries of a full warp step (the bank-aware ordering permutes a whole bucket of a run)
