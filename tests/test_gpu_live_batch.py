@@ -98,3 +98,32 @@ def test_live_batch_limits(A, pvlib):
     pv = A.phasevocoder(44100, 2, 1.0, 4.0, streams=3)
     assert pvlib.pvgpu_stream_count(pv._h) == 3
     pv.close()
+
+
+def test_live_batch_large_uses_the_copy_pool(A):
+    """300 rows and more start the row-copy pool (page-locked packing with non-temporal stores on several threads, ring FIFO
+    filled by the device-to-host copy): a few streams against their own instances, odd call sizes included, and a call larger
+    than the pool's 1 MB threshold."""
+    sr, ch, S = 44100, 1, 320
+    n = 480 * 25 + 4099
+    base = make_input("x", sr, ch, n / sr, 8100)[:, :n]
+    X = np.ascontiguousarray(np.repeat(base, S, axis=0) * (1.0 + 0.01 * np.arange(S, dtype=np.float32))[:, None])
+    live = A.phasevocoder(sr, ch, 1.0, 7.0, streams=S)
+    picks = (0, 1, 77, S - 1)
+    singles = [A.phasevocoder(sr, ch, 1.0, 7.0) for _ in picks]
+    sizes = [480] * 10 + [4099, 1, 0, 480, 311] + [480] * 12
+    pos = 0
+    for m in sizes:
+        m = min(m, n - pos)
+        live.processInData(np.ascontiguousarray(X[:, pos:pos + m]))
+        avail = live.getOutSamples()
+        Y = live.getOutData(avail)
+        for j, i in enumerate(picks):
+            singles[j].processInData(np.ascontiguousarray(X[i:i + 1, pos:pos + m]))
+            assert singles[j].getOutSamples() == avail
+            y = singles[j].getOutData(avail)
+            assert np.array_equal(_bits(Y[i:i + 1]), _bits(y)), f"stream {i} at {pos}"
+        pos += m
+    live.close()
+    for pv in singles:
+        pv.close()
