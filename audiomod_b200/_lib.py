@@ -95,6 +95,7 @@ SYMBOLS = {
     "pvgpu_test_inverse_polar": (C.c_int, [C.c_int, C.c_int, C.c_int, _fp, _fp, _fp]),
     "pvgpu_test_atan2f": (C.c_int, [C.c_int, C.c_int64, _fp, _fp, _fp]),
     "pvgpu_test_princarg": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "pvgpu_test_host_structs": (C.c_int, []),
 }
 
 _lib = None

@@ -1813,7 +1813,74 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *cons
     return PVGPU_OK;
 }
 
+// Host-only self-test of the live batch's containers (no device work): the ring FIFO across wrap-arounds and growth, the
+// row-copy pool against a serial copy, non-temporal copies at every alignment.  Returns 0 or the number of the failed check.
+static int host_structs_selftest() {
+    {   // RowFifo
+        const size_t R = 7;
+        RowFifo f;
+        f.init(R);
+        RowPool none;
+        std::vector<std::vector<float>> model(R);
+        std::vector<float> block;
+        std::vector<float *> out(R);
+        std::vector<std::vector<float>> got(R);
+        unsigned seed = 12345;
+        float next = 0.f;
+        for (int it = 0; it < 400; ++it) {
+            seed = seed * 1664525u + 1013904223u;
+            const size_t n = (seed >> 16) % (it % 50 == 49 ? 9000 : 700);
+            if (!f.reserve(f.count + n)) return 1;
+            size_t w, first;
+            f.write_span(n, &w, &first);
+            for (size_t r = 0; r < R; ++r)
+                for (size_t i = 0; i < n; ++i) {
+                    const float v = next + (float)r * 0.25f + (float)i;
+                    model[r].push_back(v);
+                    if (i < first) f.buf[r * f.cap + w + i] = v; else f.buf[r * f.cap + (i - first)] = v;
+                }
+            next += 1000.f;
+            f.commit(n);
+            seed = seed * 1664525u + 1013904223u;
+            const size_t k = std::min<size_t>(f.count, (seed >> 16) % 900);
+            for (size_t r = 0; r < R; ++r) { got[r].assign(k + 1, -1.f); out[r] = got[r].data(); }
+            f.pop(out.data(), k, none);
+            for (size_t r = 0; r < R; ++r) {
+                for (size_t i = 0; i < k; ++i) if (got[r][i] != model[r][i]) return 2;
+                if (got[r][k] != -1.f) return 3;
+                model[r].erase(model[r].begin(), model[r].begin() + (long)k);
+            }
+            if (f.count != model[0].size()) return 4;
+        }
+    }
+    {   // RowPool + copy_nt
+        RowPool pool;
+        pool.start(3);
+        const size_t R = 600, n = 1031;
+        std::vector<float> src(R * n), a(R * (n + 24), -2.f), b(R * (n + 24), -2.f);
+        for (size_t i = 0; i < src.size(); ++i) src[i] = (float)(i % 9973) * 0.5f;
+        for (int rep = 0; rep < 20; ++rep) {
+            const size_t shift = (size_t)rep % 8;   // every destination alignment
+            pool.run(R, sizeof(float) * n, [&](size_t r) { copy_nt(&a[r * (n + 24) + shift], &src[r * n], n); copy_nt_fence(); });
+            for (size_t r = 0; r < R; ++r) std::memcpy(&b[r * (n + 24) + shift], &src[r * n], sizeof(float) * n);
+            if (std::memcmp(a.data(), b.data(), sizeof(float) * a.size()) != 0) return 5;
+        }
+        size_t hits = 0;
+        std::vector<unsigned char> seen(R, 0);
+        pool.run(R, (size_t)1 << 20, [&](size_t r) { seen[r]++; });
+        for (unsigned char c : seen) hits += c;
+        if (hits != R) return 6;
+    }
+    return 0;
+}
+
 extern "C" {
+
+int pvgpu_test_host_structs(void) {
+    int rc = 0;
+    const int g = guarded([&]() -> int { rc = host_structs_selftest(); return PVGPU_OK; });
+    return g != PVGPU_OK ? -g : rc;
+}
 
 static int pvgpu_create_body(const pvgpu_config *cfg, int n_streams, pvgpu_stream **out);
 int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out) {

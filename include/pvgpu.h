@@ -226,6 +226,9 @@ int pvgpu_test_inverse_polar(int device, int fftsize, int n_frames, const float 
 int pvgpu_test_atan2f(int device, int64_t n, const float *y, const float *x, float *out);
 /* princarg (src/common/system/sys.h:84-91) */
 int pvgpu_test_princarg(int device, int64_t n, const double *a, double *out);
+/* host-only self-test of the live batch's containers (ring FIFO, row-copy pool, non-temporal copies): 0 = ok, else the number of
+ * the failed check (negative: an error code).  Needs no device. */
+int pvgpu_test_host_structs(void);
 
 #ifdef __cplusplus
 }

@@ -165,3 +165,9 @@ def test_biquad_design_matches_the_cookbook(pvlib):
     with pytest.raises(A.PvgpuError):
         A.biquad_design(9, sr, 100.0, 1.0, 0.0)
     assert len(A.equalizer_chain()) == 1 and len(A.equalizer_chain([1, 100, 1, 0] * 8)) == 8
+
+
+def test_live_batch_host_containers(pvlib):
+    """Ring FIFO (wrap-around, growth, partial pops), row-copy pool and non-temporal copies of the live batch: the library's own
+    host-only self-test (pv_engine.cu: host_structs_selftest); needs no device."""
+    assert pvlib.pvgpu_test_host_structs() == 0
