@@ -329,10 +329,11 @@ int pvgpu_bind_thread_to_device(int device) {
 namespace pvgpu {
 void copy_nt(float *dst, const float *src, size_t n) {
 #if defined(__x86_64__)
+    auto one = [&](size_t i) { int v; std::memcpy(&v, src + i, sizeof v); _mm_stream_si32(reinterpret_cast<int *>(dst + i), v); };
     size_t i = 0;
-    while (i < n && ((uintptr_t)(dst + i) & 15)) { _mm_stream_si32((int *)(dst + i), *(const int *)(src + i)); ++i; }
+    while (i < n && ((uintptr_t)(dst + i) & 15)) one(i++);
     for (; i + 4 <= n; i += 4) _mm_stream_ps(dst + i, _mm_loadu_ps(src + i));
-    for (; i < n; ++i) _mm_stream_si32((int *)(dst + i), *(const int *)(src + i));
+    for (; i < n; ++i) one(i);
 #else
     std::memcpy(dst, src, sizeof(float) * n);
 #endif
