@@ -57,6 +57,9 @@ SYMBOLS = {
     "pvgpu_create": (C.c_int, [C.POINTER(Config), _vpp]),
     "pvgpu_create_multi": (C.c_int, [C.POINTER(Config), C.c_int, _vpp]),
     "pvgpu_stream_count": (C.c_int, [C.c_void_p]),
+    "pvgpu_process_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "pvgpu_retrieve_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "pvgpu_process_block_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "pvgpu_destroy": (None, [C.c_void_p]),
     "pvgpu_process": (C.c_int, [C.c_void_p, _fpp, C.c_int]),
     "pvgpu_available": (C.c_int, [C.c_void_p]),

@@ -1621,6 +1621,17 @@ struct pvgpu_stream {
     std::vector<float> car_tail;
     int64_t in_base = 0;
     RowFifo fifo;                          // output FIFO of all rows (the reference's outbuf ring)
+    // Device-resident I/O (pvgpu_process_device / _retrieve_device): rows come from and go to device memory, everything is
+    // enqueued on the caller's stream and no call waits for the device.  The output FIFO is a ring [rows][dfifo_cap] on the
+    // device; what a call uploads is staged in one of four page-locked arenas, each guarded by an event.
+    int io_mode = 0;                       // 0 not used yet, 1 host rows, 2 device rows
+    DevBuf d_fifo;
+    size_t dfifo_cap = 0, dfifo_rd = 0, dfifo_count = 0;
+    static constexpr int kDevArenas = 4;
+    PinnedArena dev_arena[kDevArenas];
+    cudaEvent_t dev_arena_ev[kDevArenas] = {};
+    bool dev_arena_used[kDevArenas] = {};
+    unsigned dev_arena_i = 0;
     RowPool pool;                          // host copies of a live batch's rows
     double tr_us[6] = {}, tr_dev[4] = {};  // PVGPU_STREAM_TRACE=1: accumulated microseconds per phase of a call (host) and per device phase
     cudaEvent_t tr_ev[7] = {};
@@ -1632,25 +1643,51 @@ struct pvgpu_stream {
     PinnedArena arena;
     cudaStream_t st = nullptr;
     static constexpr int kF = 64;
-    ~pvgpu_stream() { if (st) cudaStreamDestroy(st); for (auto e : tr_ev) if (e) cudaEventDestroy(e); }
+    ~pvgpu_stream() {
+        if (st) cudaStreamDestroy(st);
+        for (auto e : tr_ev) if (e) cudaEventDestroy(e);
+        for (auto e : dev_arena_ev) if (e) cudaEventDestroy(e);
+    }
 };
+
+// Room for `len` samples per row in the instance's device-resident input window (rare: the window is bounded by the FFT size
+// plus one call's input): grows both buffers, keeps the content.
+static int stream_ensure_window(pvgpu_stream *s, int64_t len, cudaStream_t st) {
+    if (len <= s->in_cap) return PVGPU_OK;
+    const int R = s->R();
+    const int64_t cap = (std::max<int64_t>(2 * s->in_cap, len + 4096) + 3) & ~(int64_t)3;
+    DevBuf grown;
+    CU(grown.ensure(sizeof(float) * (size_t)R * cap));
+    if (s->dev_len > 0)
+        CU(cudaMemcpy2DAsync(grown.p, sizeof(float) * cap, s->d_inbuf[s->cur_in].p, sizeof(float) * s->in_cap, sizeof(float) * s->dev_len, R, cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    std::swap(s->d_inbuf[s->cur_in].p, grown.p);
+    std::swap(s->d_inbuf[s->cur_in].bytes, grown.bytes);
+    s->d_inbuf[s->cur_in ^ 1].release();
+    CU(s->d_inbuf[s->cur_in ^ 1].ensure(sizeof(float) * (size_t)R * cap));
+    s->in_cap = cap;
+    return PVGPU_OK;
+}
 
 // One pvgpu_process call that completed `added` new slices starting at slice k0.  Steady state: no heap allocation (the
 // vectors keep their capacity), every upload goes through the page-locked arena, one stream synchronisation at the end.
-static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *const *in, int n_new) {
+static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *const *in, int n_new, cudaStream_t user_st = nullptr) {
+    const bool dev = s->io_mode == 2;      // device rows: the input is already in the window, everything goes on the caller's stream
+    cudaStream_t const st = dev ? user_st : s->st;
     Pipeline &pl = s->pl;
     Scheduler &sc = *s->sched;
     const DevPlan &p = pl.p;
     const int C = s->cfg.channels, R = s->R();
     CU(cudaSetDevice(pl.device));
-    static const bool trace = []() { const char *v = std::getenv("PVGPU_STREAM_TRACE"); return v && v[0] == '1'; }();
+    static const bool trace_env = []() { const char *v = std::getenv("PVGPU_STREAM_TRACE"); return v && v[0] == '1'; }();
+    const bool trace = trace_env && !dev;
     auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = trace ? now() : 0.0;
     double t_mark = t_start;
     auto mark = [&](int i) { if (trace) { const double t = now(); s->tr_us[i] += t - t_mark; t_mark = t; } };
     if (trace && !s->tr_ev[0]) for (auto &e : s->tr_ev) cudaEventCreate(&e);
-    if (trace) cudaEventRecord(s->tr_ev[0], s->st);
-    if (trace) cudaEventRecord(s->tr_ev[6], s->st);
+    if (trace) cudaEventRecord(s->tr_ev[0], st);
+    if (trace) cudaEventRecord(s->tr_ev[6], st);
     const int64_t pend = (int64_t)s->pend_len + n_new;   // earlier calls' samples that completed no slice + this call's
     const int64_t len = s->dev_len + pend;
     const SliceRec &first = sc.recs()[k0 - sc.recs_base()];
@@ -1661,24 +1698,19 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *cons
         const size_t lists = p.rs_active ? (size_t)(new_out + 8 * 32 * ((added + 3) / 4 + 1) + 64) * 24 + (size_t)added * sizeof(ResampleRun) : 0;
         const size_t need = sizeof(float) * ((size_t)R * (pend + 16) + s->car_tail.size() + sc.norm().size()) + sizeof(SliceRec) * sc.recs().size() +
                             lists + (pl.d.whisper ? sizeof(float) * (size_t)added * C * p.H : 0) + 64 * 16 + sizeof(int64_t) * (2 * R + 1);
-        s->arena.reserve(need);
-        pl.arena = &s->arena;
+        PinnedArena *ar = &s->arena;
+        if (dev) {   // no call waits for the device: rotate the arenas, each is free again when the call that used it has run
+            const unsigned i = s->dev_arena_i++ % pvgpu_stream::kDevArenas;
+            if (!s->dev_arena_ev[i]) CU(cudaEventCreateWithFlags(&s->dev_arena_ev[i], cudaEventDisableTiming));
+            if (s->dev_arena_used[i]) CU(cudaEventSynchronize(s->dev_arena_ev[i]));
+            ar = &s->dev_arena[i];
+        }
+        ar->reserve(need);
+        pl.arena = ar;
         pl.staged_all = true;
     }
     int rc;
-    if (len > s->in_cap) {   // grow both window buffers (rare: the window is bounded by the FFT size plus one call's input)
-        const int64_t cap = (std::max<int64_t>(2 * s->in_cap, len + 4096) + 3) & ~(int64_t)3;
-        DevBuf grown;
-        CU(grown.ensure(sizeof(float) * (size_t)R * cap));
-        if (s->dev_len > 0)
-            CU(cudaMemcpy2DAsync(grown.p, sizeof(float) * cap, s->d_inbuf[s->cur_in].p, sizeof(float) * s->in_cap, sizeof(float) * s->dev_len, R, cudaMemcpyDeviceToDevice, s->st));
-        CU(cudaStreamSynchronize(s->st));
-        std::swap(s->d_inbuf[s->cur_in].p, grown.p);
-        std::swap(s->d_inbuf[s->cur_in].bytes, grown.bytes);
-        s->d_inbuf[s->cur_in ^ 1].release();
-        CU(s->d_inbuf[s->cur_in ^ 1].ensure(sizeof(float) * (size_t)R * cap));
-        s->in_cap = cap;
-    }
+    if ((rc = stream_ensure_window(s, len, st))) return rc;
     const int64_t in_stride = s->in_cap;
     float *d_in = s->d_inbuf[s->cur_in].as<float>();
     if (pend > 0) {
@@ -1701,26 +1733,26 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *cons
             }
         });
         mark(0);   // pack
-        if (trace) cudaEventRecord(s->tr_ev[5], s->st);
+        if (trace) cudaEventRecord(s->tr_ev[5], st);
         if (R >= 64) {
             // many short rows: one contiguous copy over PCIe, then the pitched placement on the device (a host-to-device 2-D copy
             // of 4096 rows of 1.9 KB to 4-byte-aligned destinations ran at 7 GB/s, and so did the device-to-device one)
             CU(s->d_stage.ensure(sizeof(float) * (size_t)R * pp));
-            CU(cudaMemcpyAsync(s->d_stage.p, pin, sizeof(float) * (size_t)R * pp, cudaMemcpyHostToDevice, s->st));
-            launch_place_rows(d_in + s->dev_len, in_stride, s->d_stage.as<float>(), pp, (int)pend, R, s->st);
+            CU(cudaMemcpyAsync(s->d_stage.p, pin, sizeof(float) * (size_t)R * pp, cudaMemcpyHostToDevice, st));
+            launch_place_rows(d_in + s->dev_len, in_stride, s->d_stage.as<float>(), pp, (int)pend, R, st);
         } else {
-            CU(cudaMemcpy2DAsync(d_in + s->dev_len, sizeof(float) * in_stride, pin, sizeof(float) * pp, sizeof(float) * pend, R, cudaMemcpyHostToDevice, s->st));
+            CU(cudaMemcpy2DAsync(d_in + s->dev_len, sizeof(float) * in_stride, pin, sizeof(float) * pp, sizeof(float) * pend, R, cudaMemcpyHostToDevice, st));
         }
-        if (trace) cudaEventRecord(s->tr_ev[6], s->st);   // input placed
+        if (trace) cudaEventRecord(s->tr_ev[6], st);   // input placed
     }
     // per-row limits: [0..R) valid input end, [R..2R) output limit, [2R] carrier length
     s->lim.resize(2 * (size_t)R + 1);
     for (int r = 0; r < R; ++r) { s->lim[r] = s->in_base + len; s->lim[R + r] = INT64_MAX; }
     s->lim[2 * R] = s->in_base + (int64_t)s->car_tail.size();
     CU(s->d_len.ensure(sizeof(int64_t) * (2 * (size_t)R + 1)));
-    if ((rc = pl.h2d(s->d_len.p, s->lim.data(), sizeof(int64_t) * (2 * (size_t)R + 1), s->st))) return rc;
-    if ((rc = pl.upload_schedule(sc, s->st))) return rc;
-    if ((rc = pl.build_resample_runs(k0, k0 + added, pl.fused ? pl.fa.run : ola_run_limit(p, 8, pl.max_consumed, pl.max_out), s->st))) return rc;
+    if ((rc = pl.h2d(s->d_len.p, s->lim.data(), sizeof(int64_t) * (2 * (size_t)R + 1), st))) return rc;
+    if ((rc = pl.upload_schedule(sc, st))) return rc;
+    if ((rc = pl.build_resample_runs(k0, k0 + added, pl.fused ? pl.fa.run : ola_run_limit(p, 8, pl.max_consumed, pl.max_out), st))) return rc;
     CU(s->d_out.ensure(sizeof(float) * (size_t)R * out_stride));
     if (!pl.fused && halo_of(sc.recs(), sc.recs_base(), p.rs_active ? (int)p.rs_filt_len : 1) > s->ws.Fr - s->ws.F) return fail(PVGPU_ESTATE, "too many overlapping (dropped) slices; retrieve output more often");
     DevRows g{};
@@ -1736,36 +1768,51 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *cons
         const float two_pi = 2 * M_PI;
         for (size_t i = 0; i < n; ++i) s->scratch[i] = two_pi * (float)s->rng.next() / (float)2147483647;
         CU(pl.b_whisper.ensure(sizeof(float) * n));
-        if ((rc = pl.h2d(pl.b_whisper.p, s->scratch.data(), sizeof(float) * n, s->st))) return rc;
+        if ((rc = pl.h2d(pl.b_whisper.p, s->scratch.data(), sizeof(float) * n, st))) return rc;
     }
     pl.apply_mode(g);   // after the whisper table has its final address
     if (pl.d.vocoder) {
         const int64_t clen = (int64_t)s->car_tail.size();
         CU(s->d_car.ensure(sizeof(float) * (size_t)std::max<int64_t>(clen, 1)));
-        if ((rc = pl.h2d(s->d_car.p, s->car_tail.data(), sizeof(float) * clen, s->st))) return rc;
+        if ((rc = pl.h2d(s->d_car.p, s->car_tail.data(), sizeof(float) * clen, st))) return rc;
         CU(pl.b_carmag.ensure(sizeof(float) * (size_t)added * p.Hp));
         CU(pl.b_carph.ensure(sizeof(float) * (size_t)added * p.Hp));
         DevRows gc{};
         gc.rows = 1; gc.channels = 1;
         gc.in = s->d_car.as<float>(); gc.in_stride = 0; gc.in_base = s->in_base; gc.n_in = s->d_len.as<int64_t>() + 2 * R;
         gc.mag = pl.b_carmag.as<float>(); gc.phase = pl.b_carph.as<float>(); gc.F = added;
-        launch_analyse(p, gc, k0, added, s->st);
+        launch_analyse(p, gc, k0, added, st);
     }
-    if (trace) cudaEventRecord(s->tr_ev[1], s->st);   // uploads done
+    if (trace) cudaEventRecord(s->tr_ev[1], st);   // uploads done
     for (long k = k0; k < k0 + added; k += s->ws.F)
-        if ((rc = pl.run_frames(g, k, (int)std::min<long>(s->ws.F, k0 + added - k), s->st))) return rc;
+        if ((rc = pl.run_frames(g, k, (int)std::min<long>(s->ws.F, k0 + added - k), st))) return rc;
     CU(cudaGetLastError());
-    if (trace) cudaEventRecord(s->tr_ev[2], s->st);   // kernels done
-    if (new_out > 0) {   // the output goes straight into the (page-locked) FIFO ring
+    if (trace) cudaEventRecord(s->tr_ev[2], st);   // kernels done
+    if (new_out > 0 && dev) {   // device rows: append to the device-resident ring
+        if (s->dfifo_count + (size_t)new_out > s->dfifo_cap) {   // grow (rare): stop the world, re-lay the ring out
+            size_t ncap = s->dfifo_cap ? s->dfifo_cap : 4096;
+            while (ncap < s->dfifo_count + (size_t)new_out) ncap *= 2;
+            DevBuf grown;
+            CU(grown.ensure(sizeof(float) * (size_t)R * ncap));
+            if (s->dfifo_count) launch_ring_rows(grown.as<float>(), (int64_t)ncap, 0, -1, s->d_fifo.as<float>(), (int64_t)s->dfifo_cap, (int64_t)s->dfifo_rd, (int64_t)s->dfifo_cap - 1, (int)s->dfifo_count, R, st);
+            CU(cudaStreamSynchronize(st));
+            std::swap(s->d_fifo.p, grown.p);
+            std::swap(s->d_fifo.bytes, grown.bytes);
+            s->dfifo_cap = ncap; s->dfifo_rd = 0;
+        }
+        launch_ring_rows(s->d_fifo.as<float>(), (int64_t)s->dfifo_cap, (int64_t)((s->dfifo_rd + s->dfifo_count) & (s->dfifo_cap - 1)), (int64_t)s->dfifo_cap - 1, s->d_out.as<float>(), out_stride, 0, -1,
+                         (int)new_out, R, st);
+        s->dfifo_count += (size_t)new_out;
+    } else if (new_out > 0) {   // the output goes straight into the (page-locked) FIFO ring
         if (!s->fifo.reserve(s->fifo.count + (size_t)new_out)) return fail(PVGPU_ENOMEM, "out of host memory");
         size_t w, first;
         s->fifo.write_span((size_t)new_out, &w, &first);
-        CU(cudaMemcpy2DAsync(s->fifo.buf + w, sizeof(float) * s->fifo.cap, s->d_out.p, sizeof(float) * out_stride, sizeof(float) * first, R, cudaMemcpyDeviceToHost, s->st));
+        CU(cudaMemcpy2DAsync(s->fifo.buf + w, sizeof(float) * s->fifo.cap, s->d_out.p, sizeof(float) * out_stride, sizeof(float) * first, R, cudaMemcpyDeviceToHost, st));
         if (first < (size_t)new_out)
             CU(cudaMemcpy2DAsync(s->fifo.buf, sizeof(float) * s->fifo.cap, s->d_out.as<float>() + first, sizeof(float) * out_stride, sizeof(float) * ((size_t)new_out - first), R,
-                                 cudaMemcpyDeviceToHost, s->st));
+                                 cudaMemcpyDeviceToHost, st));
     }
-    if (trace) cudaEventRecord(s->tr_ev[3], s->st);   // output copy done
+    if (trace) cudaEventRecord(s->tr_ev[3], st);   // output copy done
     // forget the input no later slice can need: the rest of the window moves to the front of the other buffer, on the device
     const long k_next = k0 + added;
     const int64_t new_base = (int64_t)k_next * p.hop;
@@ -1773,17 +1820,23 @@ static int stream_run_new(pvgpu_stream *s, long k0, int added, const float *cons
     const int64_t keep = len - dropn;
     if (dropn > 0) {
         if (keep > 0)
-            CU(cudaMemcpy2DAsync(s->d_inbuf[s->cur_in ^ 1].p, sizeof(float) * in_stride, d_in + dropn, sizeof(float) * in_stride, sizeof(float) * keep, R, cudaMemcpyDeviceToDevice, s->st));
+            CU(cudaMemcpy2DAsync(s->d_inbuf[s->cur_in ^ 1].p, sizeof(float) * in_stride, d_in + dropn, sizeof(float) * in_stride, sizeof(float) * keep, R, cudaMemcpyDeviceToDevice, st));
         s->cur_in ^= 1;
     }
-    if (trace) cudaEventRecord(s->tr_ev[4], s->st);   // window compaction done
+    if (trace) cudaEventRecord(s->tr_ev[4], st);   // window compaction done
     mark(1);   // enqueue: schedule upload, work lists, launches, copies
-    CU(cudaStreamSynchronize(s->st));   // the call's only synchronisation
+    if (dev) {
+        const unsigned i = (s->dev_arena_i - 1) % pvgpu_stream::kDevArenas;
+        CU(cudaEventRecord(s->dev_arena_ev[i], st));
+        s->dev_arena_used[i] = true;
+    } else {
+        CU(cudaStreamSynchronize(st));   // the call's only synchronisation
+    }
     mark(2);   // device
     if (trace) for (int i = 0; i < 4; ++i) { float ms = 0; cudaEventElapsedTime(&ms, s->tr_ev[i], s->tr_ev[i + 1]); s->tr_dev[i] += 1e3 * ms; }
     if (trace && pend > 0) { float ms = 0; cudaEventElapsedTime(&ms, s->tr_ev[0], s->tr_ev[5]); s->tr_dev2[0] += 1e3 * ms; cudaEventElapsedTime(&ms, s->tr_ev[5], s->tr_ev[6]); s->tr_dev2[1] += 1e3 * ms; }
     pl.staged_all = true;
-    if (new_out > 0) s->fifo.commit((size_t)new_out);
+    if (new_out > 0 && !dev) s->fifo.commit((size_t)new_out);
     s->pend_len = 0;
     s->dev_len = keep;
     if (pl.d.vocoder) s->car_tail.erase(s->car_tail.begin(), s->car_tail.begin() + std::min<int64_t>(dropn, (int64_t)s->car_tail.size()));
@@ -1922,6 +1975,7 @@ static int pvgpu_create_body(const pvgpu_config *cfg, int n_streams, pvgpu_strea
     }
     if ((rc = s->ws.ensure(s->pl, s->R(), pvgpu_stream::kF, halo))) return rc;
     if ((rc = s->ws.reset_state(s->pl, s->st))) return rc;
+    CU(cudaStreamSynchronize(s->st));   // device-row calls run on the caller's stream: the state must be in place before any of them
     *out = s.release();
     return PVGPU_OK;
 }
@@ -1945,6 +1999,8 @@ int pvgpu_process(pvgpu_stream *s, const float *const *in, int n) {
 static int pvgpu_process_body(pvgpu_stream *s, const float *const *in, int n) {
     if (!s || n < 0 || (n > 0 && !in)) return fail(PVGPU_EINVAL, "bad argument");
     if (!s->pl.d.valid_mode) { s->num_res = 0; return PVGPU_OK; }  // phasevocoder.cc:104-106: unknown mode does nothing
+    if (s->io_mode == 2) return fail(PVGPU_ESTATE, "this instance is fed device rows (pvgpu_process_device); host and device rows cannot be mixed");
+    s->io_mode = 1;
     if (s->carrier) {
         const size_t at = s->car_tail.size();
         s->car_tail.resize(at + n);
@@ -1983,6 +2039,69 @@ int pvgpu_process_block(pvgpu_stream *s, float *const *buf, int n, int *ready) {
     if (s->num_res >= n) {  // processBlockNormal, phasevocoder.cc:156-183
         const int saved = s->num_res;
         pvgpu_retrieve(s, buf, n);
+        s->num_res = saved;
+        *ready = 1;
+    } else {
+        *ready = 0;
+    }
+    return PVGPU_OK;
+}
+
+static int pvgpu_process_device_body(pvgpu_stream *s, const float *d_in, int64_t in_pitch, int n, cudaStream_t st) {
+    if (!s || n < 0 || (n > 0 && !d_in) || in_pitch < n) return fail(PVGPU_EINVAL, "bad argument");
+    if (!s->pl.d.valid_mode) { s->num_res = 0; return PVGPU_OK; }
+    if (s->io_mode == 1) return fail(PVGPU_ESTATE, "this instance is fed host rows (pvgpu_process); host and device rows cannot be mixed");
+    s->io_mode = 2;
+    CU(cudaSetDevice(s->pl.device));
+    if (s->carrier) {
+        const size_t at = s->car_tail.size();
+        s->car_tail.resize(at + n);
+        s->carrier->generate(s->car_tail.data() + at, (size_t)n);
+    }
+    const long k0 = s->sched->recs_base() + s->sched->slices();
+    const int added = s->sched->feed(n);   // the schedule does not depend on the data: no call has to wait for the device
+    int rc;
+    if (n > 0) {   // the new samples join the device-resident window right away
+        if ((rc = stream_ensure_window(s, s->dev_len + n, st))) return rc;
+        launch_place_rows(s->d_inbuf[s->cur_in].as<float>() + s->dev_len, s->in_cap, d_in, in_pitch, n, s->R(), st);
+        s->dev_len += n;
+    }
+    if (added > 0 && (rc = stream_run_new(s, k0, added, nullptr, 0, st))) return rc;
+    s->num_res = (int)s->sched->available();
+    return PVGPU_OK;
+}
+int pvgpu_process_device(pvgpu_stream *s, const float *d_in, int64_t in_pitch, int n, void *cuda_stream) {
+    return guarded([&]() -> int { return pvgpu_process_device_body(s, d_in, in_pitch, n, cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy); });
+}
+
+int pvgpu_retrieve_device(pvgpu_stream *s, float *d_out, int64_t out_pitch, int n, void *cuda_stream) {
+    if (!s || n < 0 || (n > 0 && !d_out) || out_pitch < n) return -fail(PVGPU_EINVAL, "bad argument");
+    if (s->io_mode == 1) return -fail(PVGPU_ESTATE, "this instance is fed host rows; use pvgpu_retrieve");
+    long k = std::min<long>(n, s->num_res);
+    k = std::min<long>(k, s->sched->available());
+    k = std::min<long>(k, (long)s->dfifo_count);
+    if (k > 0) {
+        if (cudaSetDevice(s->pl.device) != cudaSuccess) return -fail(PVGPU_ECUDA, "cudaSetDevice failed");
+        launch_ring_rows(d_out, out_pitch, 0, -1, s->d_fifo.as<float>(), (int64_t)s->dfifo_cap, (int64_t)s->dfifo_rd, (int64_t)s->dfifo_cap - 1, (int)k, s->R(),
+                         cuda_stream ? (cudaStream_t)cuda_stream : cudaStreamLegacy);
+        s->dfifo_rd = (s->dfifo_rd + (size_t)k) & (s->dfifo_cap - 1);
+        s->dfifo_count -= (size_t)k;
+        if (s->dfifo_count == 0) s->dfifo_rd = 0;
+    }
+    s->sched->drain(k);
+    return (int)k;
+}
+
+int pvgpu_process_block_device(pvgpu_stream *s, float *d_buf, int64_t pitch, int n, void *cuda_stream, int *ready) {
+    if (!s || !ready) return fail(PVGPU_EINVAL, "bad argument");
+    const int m = s->cfg.mode;
+    if (m == PVGPU_NORMAL_STRETCH || m < -1 || m > PVGPU_FORMANT_CEPSTRAL) { *ready = 1; return PVGPU_OK; }
+    int rc = pvgpu_process_device(s, d_buf, pitch, n, cuda_stream);
+    if (rc) return rc;
+    if (s->num_res >= n) {
+        const int saved = s->num_res;
+        const int k = pvgpu_retrieve_device(s, d_buf, pitch, n, cuda_stream);
+        if (k < 0) return -k;
         s->num_res = saved;
         *ready = 1;
     } else {

@@ -114,6 +114,21 @@ class phasevocoder:
         check(_lib.lib().pvgpu_process_block(self._h, _chan_ptrs(bufferData), n, C.byref(ready)))
         self._ready = bool(ready.value)
 
+    # ---- device rows: float32 device memory, row r at ptr + r * pitch floats; enqueued on cuda_stream, no call waits ----
+    def processInDataDevice(self, d_ptr: int, pitch: int, n: int, cuda_stream: int = 0) -> None:
+        check(_lib.lib().pvgpu_process_device(self._h, C.c_void_p(d_ptr), int(pitch), int(n), C.c_void_p(cuda_stream)))
+
+    def getOutDataDevice(self, d_ptr: int, pitch: int, n: int, cuda_stream: int = 0) -> int:
+        k = _lib.lib().pvgpu_retrieve_device(self._h, C.c_void_p(d_ptr), int(pitch), int(n), C.c_void_p(cuda_stream))
+        if k < 0:
+            check(-k)
+        return k
+
+    def processBlockDevice(self, d_ptr: int, pitch: int, n: int, cuda_stream: int = 0) -> None:
+        ready = C.c_int(0)
+        check(_lib.lib().pvgpu_process_block_device(self._h, C.c_void_p(d_ptr), int(pitch), int(n), C.c_void_p(cuda_stream), C.byref(ready)))
+        self._ready = bool(ready.value)
+
     def outputReady(self) -> bool:
         return self._ready
 

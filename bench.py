@@ -334,6 +334,35 @@ def stream_latency():
         live[str(S)] = {"p50": p50, "p99": p99, "max": float(t.max()), "calls": int(t.size), "real_time_streams": int(S * out["block_ms_of_audio"] / p99),
                         "audio_s_per_s": S * out["block_ms_of_audio"] / p50}
     out["live_batch_cfg4"] = live
+    # the same live batch fed device rows (pvgpu_process_block_device): nothing crosses PCIe and no call waits for the device, so
+    # the figure is the sustained time per call over the whole run (one synchronisation at the end) and the host time to enqueue one
+    import torch
+    devrows = {}
+    for S in (1024, 4096):
+        x = np.ascontiguousarray(np.tile(synth(2, 44100, 1.5, 1), (S, 1)))
+        x *= (1.0 + 0.001 * np.arange(S, dtype=np.float32))[:, None]
+        d = torch.from_numpy(x).cuda()
+        pv = A.phasevocoder(44100, 1, 1.0, 7.0, 0, 1, 2048, streams=S)
+        st = torch.cuda.Stream()
+        n = x.shape[1]
+        calls = (n - B) // B
+        with torch.cuda.stream(st):
+            for i in range(20):                                   # warm-up: allocations, ring growth
+                pv.processBlockDevice(d.data_ptr() + 4 * i * B, n, B, st.cuda_stream)
+            st.synchronize()
+            enq = []
+            t0 = time.perf_counter()
+            for i in range(20, calls):
+                t1 = time.perf_counter()
+                pv.processBlockDevice(d.data_ptr() + 4 * i * B, n, B, st.cuda_stream)
+                enq.append(time.perf_counter() - t1)
+            st.synchronize()
+            total = time.perf_counter() - t0
+        pv.close()
+        per_call = 1e3 * total / max(calls - 20, 1)
+        devrows[str(S)] = {"ms_per_call_sustained": per_call, "host_enqueue_ms_p50": float(np.percentile(np.array(enq) * 1e3, 50)), "calls": calls - 20,
+                           "real_time_streams": int(S * out["block_ms_of_audio"] / per_call), "audio_s_per_s": S * out["block_ms_of_audio"] / per_call}
+    out["live_batch_device_rows_cfg4"] = devrows
     return out
 
 

@@ -87,6 +87,16 @@ int pvgpu_create(const pvgpu_config *cfg, pvgpu_stream **out);
  * n_streams * channels <= 65535.  pvgpu_stream_count returns n_streams (1 for pvgpu_create). */
 int pvgpu_create_multi(const pvgpu_config *cfg, int n_streams, pvgpu_stream **out);
 int pvgpu_stream_count(const pvgpu_stream *s);
+/* Device rows: the streaming calls for audio that already lives on the GPU (a decoder, a synthesis model, another effect).
+ * d_in / d_out / d_buf point to float32 device memory of the instance's device, row r (= stream * channels + channel) at
+ * ptr + r * pitch floats.  Everything is enqueued on `cuda_stream` (NULL = the legacy default stream) and NO call waits for
+ * the device: the schedule does not depend on the data, so the counts (pvgpu_available, the return value of
+ * pvgpu_retrieve_device, *ready) are known on the host at once.  Use one stream for all calls of an instance (or order them
+ * yourself).  Same samples as the host-row calls, bit for bit (tests/test_gpu_live_batch.py).  An instance is fed either host
+ * rows or device rows, not both (PVGPU_ESTATE). */
+int pvgpu_process_device(pvgpu_stream *s, const float *d_in, int64_t in_pitch, int n, void *cuda_stream);
+int pvgpu_retrieve_device(pvgpu_stream *s, float *d_out, int64_t out_pitch, int n, void *cuda_stream);   /* returns the count, < 0: -error */
+int pvgpu_process_block_device(pvgpu_stream *s, float *d_buf, int64_t pitch, int n, void *cuda_stream, int *ready);
 /* phasevocoder::~phasevocoder (phasevocoder.cc:62-67) */
 void pvgpu_destroy(pvgpu_stream *s);
 /* modbase_offline::processInData (modbase.h:89, phasevocoder.cc:87-108): consume n samples per channel */

@@ -127,3 +127,72 @@ def test_live_batch_large_uses_the_copy_pool(A):
     live.close()
     for pv in singles:
         pv.close()
+
+
+@pytest.mark.parametrize("name", ["cfg4_shift_p7_mono", "cfg1_shift_p4_stereo", "cfg5_whisper_1024", "cfg5_chord_4096", "cfg2_stretch_1p5_4096"])
+def test_device_rows_equal_host_rows(A, name):
+    """pvgpu_process_device / _retrieve_device: rows in device memory, everything enqueued on one CUDA stream and no call waiting
+    for the device -- same counts and bit-identical samples as the host-row calls, for a live batch and odd call sizes."""
+    import torch
+    kw, sr, ch, secs, seed = next((c[1], c[2], c[3], c[4], c[5]) for c in CASES if c[0] == name)
+    tr, st, mode, core, fft = ctor_args(kw)
+    S = 6
+    n = int(sr * min(secs, 0.5))
+    X = np.ascontiguousarray(np.concatenate([make_input(name, sr, ch, n / sr, seed + 5 * i)[:, :n] for i in range(S)], axis=0))
+    R = S * ch
+    host = A.phasevocoder(sr, ch, tr, st, mode, core, fft, streams=S)
+    dev = A.phasevocoder(sr, ch, tr, st, mode, core, fft, streams=S)
+    stream = torch.cuda.Stream()
+    dX = torch.from_numpy(X).cuda()
+    pitch_out = 1 << 16
+    dY = torch.zeros((R, pitch_out), dtype=torch.float32, device="cuda")
+    sizes = [480, 480, 1, 0, 2048, 311, 4099, 480]
+    pos, k, got_host, counts = 0, 0, [], []
+    w = 0
+    with torch.cuda.stream(stream):
+        while pos < n:
+            m = min(sizes[k % len(sizes)], n - pos)
+            k += 1
+            host.processInData(np.ascontiguousarray(X[:, pos:pos + m]))
+            avail = host.getOutSamples()
+            take = avail if k % 3 else avail // 2
+            got_host.append(host.getOutData(take))
+            dev.processInDataDevice(dX.data_ptr() + 4 * pos, X.shape[1], m, stream.cuda_stream)
+            assert dev.getOutSamples() == avail, f"{name}: call {k}"
+            c = dev.getOutDataDevice(dY.data_ptr() + 4 * w, pitch_out, take, stream.cuda_stream)
+            assert c == got_host[-1].shape[1]
+            w += c
+            pos += m
+    stream.synchronize()
+    want = np.concatenate(got_host, axis=1)
+    assert want.shape[1] == w and w > 0
+    assert np.array_equal(_bits(dY[:, :w].cpu().numpy()), _bits(want)), f"{name}: device rows differ from host rows"
+    with pytest.raises(A.PvgpuError):
+        dev.processInData(np.zeros((R, 16), np.float32))       # an instance takes host rows or device rows, not both
+    host.close()
+    dev.close()
+
+
+def test_device_rows_process_block_protocol(A):
+    import torch
+    sr, S, B = 44100, 48, 480
+    n = B * 50
+    X = np.ascontiguousarray(np.concatenate([make_input("x", sr, 1, n / sr, 9100 + i)[:, :n] for i in range(S)], axis=0))
+    host = A.phasevocoder(sr, 1, 1.0, 7.0, streams=S)
+    dev = A.phasevocoder(sr, 1, 1.0, 7.0, streams=S)
+    stream = torch.cuda.Stream()
+    d = torch.from_numpy(X).cuda()
+    ready = []
+    with torch.cuda.stream(stream):
+        for pos in range(0, n, B):
+            dev.processBlockDevice(d.data_ptr() + 4 * pos, n, B, stream.cuda_stream)     # in place, block by block
+            ready.append(dev.outputReady())
+    stream.synchronize()
+    got = d.cpu().numpy()
+    for i, pos in enumerate(range(0, n, B)):
+        blk = np.ascontiguousarray(X[:, pos:pos + B])
+        host.processBlock(blk)
+        assert host.outputReady() == ready[i]
+        assert np.array_equal(_bits(got[:, pos:pos + B]), _bits(blk)), f"block {i}"
+    host.close()
+    dev.close()
