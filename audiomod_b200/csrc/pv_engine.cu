@@ -2022,6 +2022,7 @@ int pvgpu_available(const pvgpu_stream *s) { return s ? s->num_res : 0; }
 
 int pvgpu_retrieve(pvgpu_stream *s, float *const *out, int n) {
     if (!s || n < 0 || (n > 0 && !out)) return -fail(PVGPU_EINVAL, "bad argument");
+    if (s->io_mode == 2) return -fail(PVGPU_ESTATE, "this instance is fed device rows; use pvgpu_retrieve_device");
     long k = std::min<long>(n, s->num_res);  // phasevocoder.cc:111-113
     k = std::min<long>(k, s->sched->available());
     k = std::min<long>(k, (long)s->fifo.count);
