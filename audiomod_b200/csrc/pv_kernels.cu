@@ -911,6 +911,10 @@ __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const 
             const int jb = (int)(kmin - jmin) + sl;
             const int e0 = e_lo + lane;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            // the window sums of these samples: fetched now so that their latency hides behind the frame loads
+            float nr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) nr[u] = e0 + 32 * u < e_hi ? __ldg(&nrm[rel0 + e0 + 32 * u]) : 1.f;
             // frames in slice order = the reference's accumulator sequence; four frames' loads are issued together
             for (int j = T.j0[sl]; j <= jb; j += 4) {
                 float v[4][4];
@@ -932,7 +936,7 @@ __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const 
             for (int u = 0; u < 4; ++u) {
                 const int e = e0 + 32 * u;
                 if (e >= e_hi) break;
-                const float v = acc[u] / nrm[rel0 + e];
+                const float v = acc[u] / nr[u];
                 if (p.rs_active) {
                     s_in[e] = v;
                 } else if (sl >= first_run_slice && e - r0 < T.n_store[sl]) {

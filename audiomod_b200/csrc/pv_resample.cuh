@@ -79,19 +79,25 @@ __device__ __forceinline__ void resample_step(const DevPlan &p, const DevRows &g
     };
     load2(0, tqa, xa);
 #pragma unroll 1
-    for (int j = 0; j < L; j += 4) {
+    for (int j = 0; j < L - 4; j += 4) {
         load2(j + 2, tqb, xb);
         fma2(tqa, xa);
-        if (j + 4 < L) load2(j + 4, tqa, xa);
+        load2(j + 4, tqa, xa);
         fma2(tqb, xb);
     }
+    // last four taps; the outputs' cubic coefficients are fetched under them (the registers of the look-ahead stage are free now).
+    // cubic_coef (resample.c:339-351) of the entry's fraction is computed on the host with the reference's own float / double
+    // operations (Pipeline::build_resample_runs): one 16-byte load instead of ~30 instructions incl. three FP64 adds per output
+    load2(L - 2, tqb, xb);
+    float4 ic[ROWS];
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) ic[u] = __ldg(reinterpret_cast<const float4 *>(frac_tab) + (first + lane + 32 * u));   // padding entries hold zeros
+    fma2(tqa, xa);
+    fma2(tqb, xb);
 #pragma unroll
     for (int u = 0; u < ROWS; ++u) {
         if (!live[u]) continue;
-        // cubic_coef (resample.c:339-351) of the entry's fraction, computed on the host with the reference's own float / double
-        // operations (Pipeline::build_resample_runs): one 16-byte load instead of ~30 instructions incl. three FP64 adds per output
-        const float4 ic = __ldg(reinterpret_cast<const float4 *>(frac_tab) + (first + lane + 32 * u));
-        pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), (ic.x * acc[u][0].x) + (ic.y * acc[u][0].y) + (ic.z * acc[u][1].x) + (ic.w * acc[u][1].y));
+        pcm_store(g.out, g.fmt, orow + (ent[u] & 0xffffu), (ic[u].x * acc[u][0].x) + (ic[u].y * acc[u][0].y) + (ic[u].z * acc[u][1].x) + (ic[u].w * acc[u][1].y));
     }
 }
 
