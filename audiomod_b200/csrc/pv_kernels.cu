@@ -769,7 +769,7 @@ __global__ void k_synthesise(const DevPlan p, const DevRows g, const float *__re
 // kLock: Cartesian spectra of the phase-locked core only (g.synth_kind == 4), no other mode's code; kWarp: + the formant /
 // gender frequency warp (p.warp_tab)
 template <int N, bool kLock, bool kWarp>
-__global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256)) k_synthesise_t(const DevPlan p, const DevRows g, const float *__restrict__ car_mag,
+__global__ void __launch_bounds__((N / 32 > 256 ? N / 32 : 256), 4) k_synthesise_t(const DevPlan p, const DevRows g, const float *__restrict__ car_mag,
                                                                                  const float *__restrict__ car_phase, long k0, int nf, int total) {
     constexpr int NC = N / 2;
     using S = FftShape<NC>;

@@ -112,11 +112,13 @@ __device__ __forceinline__ void synth_prepass_lock(const DevPlan &p, const DevRo
     // formant / gender modes: freqCompSlice (:842-923) as a gather -- target bin i takes the locked bin src(i) turned by
     // 2*pi*hop*(i - src)/N and scaled by the fixed gain; the host tabulates (gain cos, gain sin, src) per target bin
     const float4 *__restrict__ wt = kWarp ? p.warp_tab : nullptr;
-#pragma unroll 1
-    for (int q0 = 0; q0 < Q; q0 += U) {
-        float2 lo[U], hi[U];
-        int sl[U], sh[U];
-        float2 wl[U], wh[U];
+    // The loads of a frame form a chain -- frame header (locked or not), bin -> region (lock_map), region -> rotation (lock_csn)
+    // -- and a thread has nothing else to do until they are back, so the chain is kept as short as it can be: the region and
+    // rotation loads do not wait for the header (they are issued for every frame from clamped indices; a frame that is not
+    // locked ignores them), and the region loads of the next group of bins are issued one group ahead.
+    const unsigned pk_max = (unsigned)(g.maxpk - 1);
+    unsigned ml_n[U], mh_n[U];   // region of this group's bins, loaded one group ahead
+    auto src_bins = [&](int q0, int (&sl)[U], int (&sh)[U], float2 (&wl)[U], float2 (&wh)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int kk = t + T * (q0 + u);
@@ -127,12 +129,26 @@ __device__ __forceinline__ void synth_prepass_lock(const DevPlan &p, const DevRo
                 wl[u] = make_float2(a4.x, a4.y); wh[u] = make_float2(b4.x, b4.y);
             }
         }
+    };
+    {
+        int sl[U], sh[U];
+        float2 wl[U], wh[U];
+        src_bins(0, sl, sh, wl, wh);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { ml_n[u] = lmap[min(sl[u], NC - 1)]; mh_n[u] = lmap[min(sh[u], NC - 1)]; }
+    }
+#pragma unroll 1
+    for (int q0 = 0; q0 < Q; q0 += U) {
+        float2 lo[U], hi[U];
+        int sl[U], sh[U];
+        float2 wl[U], wh[U];
+        src_bins(q0, sl, sh, wl, wh);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             lo[u] = make_float2(gre[sl[u]], gim[sl[u]]);
             hi[u] = make_float2(gre[sh[u]], gim[sh[u]]);
         }
-        if (locked) {
+        {
             // Two dependent gathers per bin (bin -> region -> rotation).  All region loads are issued first, then all rotation
             // loads, unconditionally from clamped indices, and the exceptions are patched afterwards.  Left to itself ptxas may
             // issue each rotation load right behind its own region load to save registers, which serialises the chains
@@ -144,8 +160,8 @@ __device__ __forceinline__ void synth_prepass_lock(const DevPlan &p, const DevRo
             float2 cl[U], ch[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                ml[u] = lmap[kWarp ? min(sl[u], NC - 1) : sl[u]];
-                mh[u] = lmap[min(sh[u], NC - 1)];
+                ml[u] = min(ml_n[u], pk_max);
+                mh[u] = min(mh_n[u], pk_max);
                 all |= ml[u] | mh[u];
             }
             // every rotation address depends on every region index (through a mask that is zero at run time, which the compiler
@@ -156,15 +172,24 @@ __device__ __forceinline__ void synth_prepass_lock(const DevPlan &p, const DevRo
                 cl[u] = lcsn[ml[u] + tie];
                 ch[u] = lcsn[mh[u] + tie];
             }
+            if (q0 + U < Q) {   // the next group's regions, behind this group's rotation loads
+                int sl2[U], sh2[U];
+                float2 wl2[U], wh2[U];
+                src_bins(q0 + U, sl2, sh2, wl2, wh2);
+#pragma unroll
+                for (int u = 0; u < U; ++u) { ml_n[u] = lmap[min(sl2[u], NC - 1)]; mh_n[u] = lmap[min(sh2[u], NC - 1)]; }
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (kWarp && sl[u] >= NC) cl[u] = make_float2(1.f, 0.f);
                 if (sh[u] >= NC) ch[u] = make_float2(1.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                lo[u] = make_float2(lo[u].x * cl[u].x - lo[u].y * cl[u].y, lo[u].x * cl[u].y + lo[u].y * cl[u].x);
-                hi[u] = make_float2(hi[u].x * ch[u].x - hi[u].y * ch[u].y, hi[u].x * ch[u].y + hi[u].y * ch[u].x);
+            for (int u = 0; u < U; ++u) {   // a frame that is not locked keeps its bins as they are (selected, not multiplied by one)
+                const float2 rl = make_float2(lo[u].x * cl[u].x - lo[u].y * cl[u].y, lo[u].x * cl[u].y + lo[u].y * cl[u].x);
+                const float2 rh = make_float2(hi[u].x * ch[u].x - hi[u].y * ch[u].y, hi[u].x * ch[u].y + hi[u].y * ch[u].x);
+                lo[u] = locked ? rl : lo[u];
+                hi[u] = locked ? rh : hi[u];
             }
         }
         if (kWarp) {

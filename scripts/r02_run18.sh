@@ -1,7 +1,7 @@
 #!/bin/bash
 # host-computed cubic coefficients of the resampler: tests, then A/B against the previous build (ab/libpvgpu_base.so)
 out=gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fused.py tests/test_gpu_live_batch.py -q -x > $out/r02ah_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fused.py tests/test_gpu_fullsize.py -q -x > $out/r02ah_pytest.log 2>&1
 echo "== all gpu tests: $(tail -1 $out/r02ah_pytest.log)"; grep -E "^(FAILED|ERROR)" $out/r02ah_pytest.log | head -5
 short="--steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-latency"
 line() {
