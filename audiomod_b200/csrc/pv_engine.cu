@@ -401,6 +401,15 @@ struct Pipeline {
             hdr.u_lo = std::max<int64_t>(0, ra.res_off + ra.rs_last - L + 1);
             hdr.out_first = ra.out_off;
             hdr.ent_off = (int)ent.size();
+            {   // the walk k_ola_resample does over the records (same bounds), done once here
+                const int64_t u_lo_raw = ra.res_off + ra.rs_last - L + 1;
+                long kmin = ka;
+                while (kmin > recs_base && kmin > 0 && h_recs[kmin - recs_base].res_off > u_lo_raw && ka - kmin < ola_max_table_slices() - run - 1) --kmin;
+                const long jmin = h_recs[kmin - recs_base].jlo;
+                hdr.back_slices = (int)(ka - kmin);
+                hdr.back_frames = (int)(ka - jmin);
+                hdr.ola_base = h_recs[jmin - recs_base].ola_off;
+            }
             for (int q = 0; q < nb; ++q) { be[q].clear(); bf[q].clear(); }
             for (long k = ka; k < kb; ++k) {
                 const SliceRec &r = h_recs[k - recs_base];
@@ -424,7 +433,6 @@ struct Pipeline {
             }
             int pos = 0;
             for (int q = 0; q < nb; ++q) {
-                hdr.start[q] = pos;
                 // A warp step takes kResBlock consecutive entries as kResPerThread rows of 32 lanes, and a row's 32 input windows are
                 // read with one shared-memory load per tap: permute the entries (two blocks at a time) so that the windows of a row
                 // start on different banks (start mod 32) as far as possible.  The order of the entries is otherwise free (each carries its
@@ -475,7 +483,6 @@ struct Pipeline {
                     run_steps.push_back((unsigned)(r0 * 32) | ((unsigned)(rows - 1) << 20) | ((unsigned)q << 24));
                 }
             }
-            for (int q = nb; q <= kMaxBuckets; ++q) hdr.start[q] = pos;
             hdr.padded = pos;
             // long steps first: the CTA's warps take the steps round-robin
             std::stable_sort(run_steps.begin(), run_steps.end(), [](unsigned a, unsigned b) { return ((a >> 20) & 7u) > ((b >> 20) & 7u); });

@@ -855,14 +855,24 @@ __global__ void __launch_bounds__(256, 4) k_ola_resample(const DevPlan p, const 
     // few records back; the loads are uniform and cached)
     const int N = p.N;
     const SliceRec *__restrict__ rr = recs - recs_base;
-    const int64_t u_lo_raw = p.rs_active ? rr[ka].res_off + rr[ka].rs_last - L + 1 : rr[ka].res_off;
-    long kmin = ka;
-    while (kmin > recs_base && kmin > 0 && rr[kmin].res_off > u_lo_raw && ka - kmin < kOlaMaxSlices - run - 1) --kmin;
-    const long jmin = rr[kmin].jlo;
+    long kmin, jmin;
+    int64_t ola_base, u_lo;
+    if (p.rs_active) {   // the host has walked the records (ResampleRun): one load instead of a chain of four
+        const ResampleRun *__restrict__ h = &runs[(ka - run_origin) / run];
+        kmin = ka - __ldg(&h->back_slices);
+        jmin = ka - __ldg(&h->back_frames);
+        ola_base = __ldg((const long long *)&h->ola_base);
+        u_lo = __ldg((const long long *)&h->u_lo);
+    } else {
+        const int64_t u_lo_raw = rr[ka].res_off;
+        kmin = ka;
+        while (kmin > recs_base && kmin > 0 && rr[kmin].res_off > u_lo_raw && ka - kmin < kOlaMaxSlices - run - 1) --kmin;
+        jmin = rr[kmin].jlo;
+        ola_base = rr[jmin].ola_off;
+        u_lo = u_lo_raw < 0 ? 0 : u_lo_raw;
+    }
     const int nsl = (int)(kb - kmin);
     const int nfr = min((int)(kb - jmin), kOlaMaxFrames);   // the host's halo check keeps kb - jmin within the table
-    const int64_t ola_base = rr[jmin].ola_off;
-    const int64_t u_lo = u_lo_raw < 0 ? 0 : u_lo_raw;
     const int64_t u_hi = rr[kb - 1].res_off + ((rr[kb - 1].flags & 1) ? 0 : rr[kb - 1].consumed);
     const int span = (int)min(u_hi - u_lo, (int64_t)max_in);
     const int64_t out_first = rr[ka].out_off;

@@ -98,7 +98,11 @@ struct ResampleRun {
     int64_t out_first;   // output position of the run's first slice
     int ent_off;         // offset of the run's entries in rs_ent / rs_frac
     int padded;          // entries including padding
-    int start[kMaxBuckets + 1];
+    // what k_ola_resample would otherwise find by walking the slice records (four dependent loads before its tables can be filled):
+    int64_t ola_base;    // ola_off of the first frame overlapping the run's slices and its resampler history
+    int back_slices;     // ka - kmin: slices before the run that hold its resampler history
+    int back_frames;     // ka - jmin: frames before the run's first slice that overlap those
+    int rsv[5];
     int step_off;        // offset of the run's warp steps in rs_steps
     int n_steps;         // step = entry offset within the run | (rows - 1) << 20 | table phase << 24, rows <= kResPerThread
     int pad[1];
